@@ -1,0 +1,52 @@
+// Shared device helpers for the gSCAN sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define GSCAN_CHECK_LAUNCH()                         \
+  do {                                               \
+    cudaError_t e__ = cudaGetLastError();            \
+    if (e__ != cudaSuccess) return (int)e__;         \
+  } while (0)
+
+namespace gscan {
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// tanh / sigmoid with ~1e-7 absolute error: one ex2.approx + one rcp.approx on the SFU instead
+// of libm's ~25-instruction tanhf.  The attention scores need (Ti + G*G) * H tanh per example per
+// decoder step, which makes the SFU the second-busiest pipe of the recurrent sweep.
+#ifdef GSCAN_PRECISE_MATH
+__device__ __forceinline__ float act_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+#else
+__device__ __forceinline__ float act_tanh(float x) {
+  // 1 - 2/(1+e^{2x}); saturates correctly: e -> inf gives 1, e -> 0 gives -1
+  float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, 1.0f + e);
+}
+__device__ __forceinline__ float act_sigmoid(float x) {
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+#endif
+
+// Packed fp32 FMA (FFMA2, new on sm_100): two independent IEEE fp32 FMAs per issue slot.
+__device__ __forceinline__ void fma2(float2& acc, const float2 a, const float2 b) {
+  acc = __ffma2_rn(a, b, acc);
+}
+
+__host__ __device__ __forceinline__ int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace gscan

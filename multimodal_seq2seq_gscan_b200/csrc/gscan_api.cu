@@ -1,0 +1,753 @@
+// C ABI of libgscan_b200.so (see include/gscan_b200.h): workspace layout and the launch
+// sequences for forward / backward / encode / decode-step / greedy decode.
+#include "../../include/gscan_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "cnn.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "misc.cuh"
+#include "recurrent.cuh"
+
+using namespace gscan;
+
+#define TRY(expr)                \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != 0) return rc__;  \
+  } while (0)
+#define TRYCUDA(expr)                            \
+  do {                                           \
+    cudaError_t e__ = (expr);                    \
+    if (e__ != cudaSuccess) return (int)e__;     \
+  } while (0)
+
+namespace {
+
+constexpr size_t kMaxSmemBytes = 227 * 1024;
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- workspace layout --------------------------------------------------------------------
+struct Layout {
+  size_t total = 0;
+  size_t take(size_t n) {
+    size_t o = total;
+    total += (n + 3) & ~size_t(3);
+    return o;
+  }
+  // forward (saved)
+  size_t Wt_cnn, feat, KV, enc_x, xg[2], enc_h[2], enc_c[2], enc_g[2], enc_out, h_enc, KT, h0;
+  size_t WA_t, WB_t, WC_t, WD_t, WhhE_t[2];
+  size_t U, Xe, Cs, gates, alpha, beta, Qp, qT, qV, beta_sum, aux_logp, pre, logp;
+  // backward scratch
+  size_t dlogits, dpre, dU, dgates, dd, dqV, dqT, dKT, dKV, dh0, dbeta_aux, dfeat, dconv, dWt_cnn;
+  size_t denc_out, dh_enc, dpre0, dga[2], hprev[2], denc_x, dvec;
+  int RA, RB;
+};
+
+Layout make_layout(const gscan_dims& d, bool with_backward) {
+  Layout L;
+  const size_t B = d.B, Ti = d.Ti, Tt = d.Tt, M = (size_t)d.G * d.G, D = 3 * (size_t)d.F, H = d.H, E = d.E, V = d.V;
+  CnnShape cs{d.B, d.G, d.C, d.F, d.K3};
+  L.RA = (int)(H + (d.conditional_attention ? H : 0) + 4 * H);
+  L.RB = (int)((d.conditional_attention ? H : 0) + 4 * H);
+  L.Wt_cnn = L.take(cs.wtotal());
+  L.feat = L.take(B * M * D);
+  L.KV = L.take(B * M * H);
+  L.enc_x = L.take(B * Ti * E);
+  for (int i = 0; i < 2; ++i) L.xg[i] = L.take(B * Ti * 4 * H);
+  for (int i = 0; i < 2; ++i) L.enc_h[i] = L.take(Ti * B * H);
+  for (int i = 0; i < 2; ++i) L.enc_c[i] = L.take(Ti * B * H);
+  for (int i = 0; i < 2; ++i) L.enc_g[i] = L.take(Ti * B * 4 * H);
+  L.enc_out = L.take(Ti * B * H);
+  L.h_enc = L.take(B * H);
+  L.KT = L.take(Ti * B * H);
+  L.h0 = L.take(B * H);
+  L.WA_t = L.take(H * L.RA);
+  L.WB_t = L.take(H * L.RB);
+  L.WC_t = L.take(H * H);
+  L.WD_t = L.take(H * 4 * H);
+  for (int i = 0; i < 2; ++i) L.WhhE_t[i] = L.take(H * 4 * H);
+  L.U = L.take((Tt + 1) * B * 4 * H);
+  L.Xe = L.take(Tt * B * 4 * H);
+  L.Cs = L.take((Tt + 1) * B * H);
+  L.gates = L.take(Tt * B * 4 * H);
+  L.alpha = L.take(Tt * B * Ti);
+  L.beta = L.take(Tt * B * M);
+  L.Qp = L.take(Tt * B * H);
+  L.qT = L.take(Tt * B * H);
+  L.qV = L.take(Tt * B * H);
+  L.beta_sum = L.take(B * M);
+  L.aux_logp = L.take(B * M);
+  L.pre = L.take(Tt * B * H);
+  L.logp = L.take(B * Tt * V);
+  if (with_backward) {
+    L.dlogits = L.take(Tt * B * V);
+    L.dpre = L.take(Tt * B * H);
+    L.dU = L.take(Tt * B * 4 * H);
+    L.dgates = L.take(Tt * B * 4 * H);
+    L.dd = L.take(Tt * B * H);
+    L.dqV = L.take(Tt * B * H);
+    L.dqT = L.take(Tt * B * H);
+    L.dKT = L.take(Ti * B * H);
+    L.dKV = L.take(B * M * H);
+    L.dh0 = L.take(B * H);
+    L.dbeta_aux = L.take(B * M);
+    L.dfeat = L.take(B * M * D);
+    L.dconv = L.take(B * M * D);
+    L.dWt_cnn = L.take(cs.wtotal());
+    L.denc_out = L.take(Ti * B * H);
+    L.dh_enc = L.take(B * H);
+    L.dpre0 = L.take(B * H);
+    for (int i = 0; i < 2; ++i) L.dga[i] = L.take(B * Ti * 4 * H);
+    for (int i = 0; i < 2; ++i) L.hprev[i] = L.take(B * Ti * H);
+    L.denc_x = L.take(B * Ti * E);
+    L.dvec = L.take(2 * H);
+  }
+  return L;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---- examples per CTA for the recurrent sweeps ---------------------------------------------
+int env_nb() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("GSCAN_NB");
+    v = s ? atoi(s) : 0;
+  }
+  return v;
+}
+
+template <int NB>
+size_t dec_smem_bytes(const gscan_dims& d, int RA, int RB, bool bwd, bool greedy) {
+  const int M = d.G * d.G;
+  size_t f = bwd ? dec_bwd_smem_floats<NB>(d.Ti, M, d.H, kRecThreads)
+                 : dec_fwd_smem_floats<NB>(d.Ti, M, d.H, RA, RB, pad4(d.V), greedy, kRecThreads);
+  return f * sizeof(float);
+}
+
+// returns 4, 2, 1 or 0 (nothing fits)
+int pick_nb(const gscan_dims& d, int RA, int RB, bool bwd, bool greedy) {
+  int want = env_nb();
+  if (want != 1 && want != 2 && want != 4) want = (d.B > 2 * num_sms()) ? 4 : 2;
+  for (int nb = want; nb >= 1; nb >>= 1) {
+    if (nb * d.H > kRecThreads) continue;
+    size_t bytes = nb == 4 ? dec_smem_bytes<4>(d, RA, RB, bwd, greedy)
+                 : nb == 2 ? dec_smem_bytes<2>(d, RA, RB, bwd, greedy)
+                           : dec_smem_bytes<1>(d, RA, RB, bwd, greedy);
+    if (bytes <= kMaxSmemBytes) return nb;
+  }
+  return 0;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  TRYCUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int NB, bool GREEDY>
+int launch_dec_fwd_t(const DecFwdP& p, size_t bytes, cudaStream_t st) {
+  TRY(set_smem(decoder_fwd_kernel<NB, GREEDY>, bytes));
+  decoder_fwd_kernel<NB, GREEDY><<<ceil_div(p.B, NB), kRecThreads, bytes, st>>>(p);
+  GSCAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_dec_fwd(const gscan_dims& d, const DecFwdP& p, bool greedy, cudaStream_t st) {
+  int nb = pick_nb(d, p.RA, p.RB, false, greedy);
+  if (nb == 0) return GSCAN_E_UNSUPPORTED;
+  if (nb == 4) {
+    size_t by = dec_smem_bytes<4>(d, p.RA, p.RB, false, greedy);
+    return greedy ? launch_dec_fwd_t<4, true>(p, by, st) : launch_dec_fwd_t<4, false>(p, by, st);
+  } else if (nb == 2) {
+    size_t by = dec_smem_bytes<2>(d, p.RA, p.RB, false, greedy);
+    return greedy ? launch_dec_fwd_t<2, true>(p, by, st) : launch_dec_fwd_t<2, false>(p, by, st);
+  }
+  size_t by = dec_smem_bytes<1>(d, p.RA, p.RB, false, greedy);
+  return greedy ? launch_dec_fwd_t<1, true>(p, by, st) : launch_dec_fwd_t<1, false>(p, by, st);
+}
+
+template <int NB>
+int launch_dec_bwd_t(const DecBwdP& p, size_t bytes, cudaStream_t st) {
+  TRY(set_smem(decoder_bwd_kernel<NB>, bytes));
+  decoder_bwd_kernel<NB><<<ceil_div(p.B, NB), kRecThreads, bytes, st>>>(p);
+  GSCAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_dec_bwd(const gscan_dims& d, const DecBwdP& p, cudaStream_t st) {
+  int nb = pick_nb(d, 0, 0, true, false);
+  if (nb == 0) return GSCAN_E_UNSUPPORTED;
+  if (nb == 4) return launch_dec_bwd_t<4>(p, dec_smem_bytes<4>(d, 0, 0, true, false), st);
+  if (nb == 2) return launch_dec_bwd_t<2>(p, dec_smem_bytes<2>(d, 0, 0, true, false), st);
+  return launch_dec_bwd_t<1>(p, dec_smem_bytes<1>(d, 0, 0, true, false), st);
+}
+
+int enc_nb(const gscan_dims& d) {
+  int nb = 2;
+  while (nb > 1 && nb * d.H > kRecThreads) nb >>= 1;
+  return nb;
+}
+
+int launch_enc(const gscan_dims& d, const EncP& p, bool bwd, cudaStream_t st) {
+  int nb = enc_nb(d);
+  dim3 grid(ceil_div(d.B, nb), 2);
+  if (nb == 2) {
+    size_t by = enc_smem_floats<2>(d.H, kRecThreads, bwd) * sizeof(float);
+    if (by > kMaxSmemBytes) return GSCAN_E_UNSUPPORTED;
+    if (bwd) { TRY(set_smem(encoder_bwd_kernel<2>, by)); encoder_bwd_kernel<2><<<grid, kRecThreads, by, st>>>(p); }
+    else { TRY(set_smem(encoder_fwd_kernel<2>, by)); encoder_fwd_kernel<2><<<grid, kRecThreads, by, st>>>(p); }
+  } else {
+    size_t by = enc_smem_floats<1>(d.H, kRecThreads, bwd) * sizeof(float);
+    if (by > kMaxSmemBytes) return GSCAN_E_UNSUPPORTED;
+    if (bwd) { TRY(set_smem(encoder_bwd_kernel<1>, by)); encoder_bwd_kernel<1><<<grid, kRecThreads, by, st>>>(p); }
+    else { TRY(set_smem(encoder_fwd_kernel<1>, by)); encoder_fwd_kernel<1><<<grid, kRecThreads, by, st>>>(p); }
+  }
+  GSCAN_CHECK_LAUNCH();
+  return 0;
+}
+
+int check_common(const gscan_dims* d, const float* const* params) {
+  if (!d || !params) return GSCAN_E_BADARG;
+  TRY(gscan_check_dims(d));
+  for (int i = 0; i < GSCAN_NUM_PARAMS; ++i) {
+    bool optional = (i == GSCAN_P_COND_W || i == GSCAN_P_COND_B) && !d->conditional_attention;
+    if (!optional && !params[i]) return GSCAN_E_BADARG;
+    if (params[i] && !aligned16(params[i])) return GSCAN_E_UNSUPPORTED;
+  }
+  return 0;
+}
+
+// NT product: C[M,N] = act(A[M,K] (lda) . W[N,K]^T (ldw) + bias + bias2)
+int linear(const float* A, long lda, const float* W, long ldw, float* C, long ldc, int M, int N, int K,
+           const float* bias, const float* bias2, int act, cudaStream_t st) {
+  return launch_sgemm(A, lda, 1, W, 1, ldw, C, ldc, M, N, K, bias, bias2, act, 0, 1, st);
+}
+// NN product: C[M,N] (+)= A[M,K] (lda) . W[K,N] (ldw)
+int matmul_nn(const float* A, long lda, const float* W, long ldw, float* C, long ldc, int M, int N, int K,
+              int accumulate, cudaStream_t st) {
+  return launch_sgemm(A, lda, 1, W, ldw, 1, C, ldc, M, N, K, nullptr, nullptr, 0, accumulate, 1, st);
+}
+
+int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* situations, const float* drop_cnn,
+                    float* Wt, float* feat, cudaStream_t st) {
+  CnnShape cs{d.B, d.G, d.C, d.F, d.K3};
+  cnn_relayout_kernel<<<ceil_div(cs.wtotal(), 256), 256, 0, st>>>(
+      cs, const_cast<float*>(P[GSCAN_P_CONV1_W]), const_cast<float*>(P[GSCAN_P_CONV2_W]),
+      const_cast<float*>(P[GSCAN_P_CONV3_W]), Wt, 1);
+  GSCAN_CHECK_LAUNCH();
+  size_t smem = (size_t)cs.M() * cs.C * 8;
+  if (smem > 48 * 1024) TRY(set_smem(cnn_forward_kernel, smem));
+  cnn_forward_kernel<<<d.B, 256, smem, st>>>(cs, situations, Wt, P[GSCAN_P_CONV1_B], P[GSCAN_P_CONV2_B],
+                                             P[GSCAN_P_CONV3_B], drop_cnn, feat);
+  GSCAN_CHECK_LAUNCH();
+  return 0;
+}
+
+// CNN + visual keys + encoder + textual keys + initial decoder state, shared by forward / encode / greedy.
+int run_encoder_side(const gscan_dims& d, const float* const* P, const long long* commands, const int* cmd_len,
+                     const float* situations, const float* drop_cnn, const float* drop_enc, float* ws,
+                     const Layout& L, bool need_keys, cudaStream_t st) {
+  const int B = d.B, Ti = d.Ti, M = d.G * d.G, D = 3 * d.F, H = d.H, E = d.E;
+  TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, st));
+  if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, st));
+  // command embeddings and their input-gate pre-activations for both directions
+  {
+    long n = (long)B * Ti * E;
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(commands, d.Ti_stride, P[GSCAN_P_ENC_EMB], E, drop_enc,
+                                                              ws + L.enc_x, E, B, Ti, 0);
+    GSCAN_CHECK_LAUNCH();
+  }
+  TRY(linear(ws + L.enc_x, E, P[GSCAN_P_ENC_WIH], E, ws + L.xg[0], 4 * H, B * Ti, 4 * H, E, P[GSCAN_P_ENC_BIH],
+             P[GSCAN_P_ENC_BHH], 0, st));
+  TRY(linear(ws + L.enc_x, E, P[GSCAN_P_ENC_WIH_R], E, ws + L.xg[1], 4 * H, B * Ti, 4 * H, E, P[GSCAN_P_ENC_BIH_R],
+             P[GSCAN_P_ENC_BHH_R], 0, st));
+  {
+    PackTable tab;
+    tab.n = 2;
+    tab.d[0] = PackDesc{P[GSCAN_P_ENC_WHH], H, 0, ws + L.WhhE_t[0], 4 * H, 0, 4 * H, H};
+    tab.d[1] = PackDesc{P[GSCAN_P_ENC_WHH_R], H, 0, ws + L.WhhE_t[1], 4 * H, 0, 4 * H, H};
+    TRY(launch_pack(tab, st));
+  }
+  TRYCUDA(cudaMemsetAsync(ws + L.enc_out, 0, sizeof(float) * (size_t)Ti * B * H, st));
+  TRYCUDA(cudaMemsetAsync(ws + L.h_enc, 0, sizeof(float) * (size_t)B * H, st));
+  EncP ep{};
+  ep.B = B; ep.Ti = Ti; ep.H = H;
+  for (int i = 0; i < 2; ++i) {
+    ep.Whh_t[i] = ws + L.WhhE_t[i];
+    ep.xg[i] = ws + L.xg[i];
+    ep.enc_h[i] = ws + L.enc_h[i];
+    ep.enc_c[i] = ws + L.enc_c[i];
+    ep.enc_g[i] = ws + L.enc_g[i];
+  }
+  ep.len = cmd_len;
+  ep.enc_out = ws + L.enc_out;
+  ep.h_enc = ws + L.h_enc;
+  TRY(launch_enc(d, ep, false, st));
+  if (need_keys) {
+    TRY(linear(ws + L.enc_out, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.KT, H, Ti * B, H, H, nullptr, nullptr, 0, st));
+    TRY(linear(ws + L.h_enc, H, P[GSCAN_P_E2D_W], H, ws + L.h0, H, B, H, H, P[GSCAN_P_E2D_B], nullptr, 1, st));
+  }
+  return 0;
+}
+
+int pack_decoder_weights(const gscan_dims& d, const float* const* P, float* ws, const Layout& L, cudaStream_t st) {
+  const int H = d.H;
+  PackTable tab;
+  int n = 0;
+  int r = 0;
+  tab.d[n++] = PackDesc{P[GSCAN_P_TXT_QUERY_W], H, 0, ws + L.WA_t, L.RA, r, H, H}; r += H;
+  if (d.conditional_attention) { tab.d[n++] = PackDesc{P[GSCAN_P_COND_W], 2 * H, 0, ws + L.WA_t, L.RA, r, H, H}; r += H; }
+  tab.d[n++] = PackDesc{P[GSCAN_P_DEC_WHH], H, 0, ws + L.WA_t, L.RA, r, 4 * H, H};
+  r = 0;
+  if (d.conditional_attention) { tab.d[n++] = PackDesc{P[GSCAN_P_COND_W], 2 * H, H, ws + L.WB_t, L.RB, r, H, H}; r += H; }
+  tab.d[n++] = PackDesc{P[GSCAN_P_DEC_WIH], 3 * H, H, ws + L.WB_t, L.RB, r, 4 * H, H};
+  tab.d[n++] = PackDesc{P[GSCAN_P_VIS_QUERY_W], H, 0, ws + L.WC_t, H, 0, H, H};
+  tab.d[n++] = PackDesc{P[GSCAN_P_DEC_WIH], 3 * H, 2 * H, ws + L.WD_t, 4 * H, 0, 4 * H, H};
+  tab.n = n;
+  return launch_pack(tab, st);
+}
+
+void fill_dec_fwd_common(const gscan_dims& d, const float* const* P, float* ws, const Layout& L, DecFwdP& p) {
+  p.B = d.B; p.Ti = d.Ti; p.M = d.G * d.G; p.H = d.H; p.V = d.V; p.cond = d.conditional_attention;
+  p.WA_t = ws + L.WA_t; p.RA = L.RA;
+  p.WB_t = ws + L.WB_t; p.RB = L.RB;
+  p.WC_t = ws + L.WC_t;
+  p.WD_t = ws + L.WD_t;
+  p.vT = P[GSCAN_P_TXT_ENERGY_W];
+  p.vV = P[GSCAN_P_VIS_ENERGY_W];
+  p.bc = P[GSCAN_P_COND_B];
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int gscan_abi_version(void) { return GSCAN_ABI_VERSION; }
+
+int gscan_check_dims(const gscan_dims* d) {
+  if (!d) return GSCAN_E_BADARG;
+  if (d->B < 1 || d->Ti < 1 || d->Tt < 1 || d->G < 1 || d->C < 1 || d->F < 1 || d->K3 < 1 || d->E < 1 || d->H < 4 ||
+      d->Vi < 1 || d->V < 1 || d->Ti_stride < d->Ti)
+    return GSCAN_E_BADARG;
+  if (d->H % 4 != 0 || d->H > kRecThreads) return GSCAN_E_UNSUPPORTED;
+  if ((d->K3 & 1) == 0) return GSCAN_E_UNSUPPORTED;            // 'same' padding k//2 needs odd k
+  if (d->V > 32 * kMaxVPerLane) return GSCAN_E_UNSUPPORTED;
+  if ((size_t)d->G * d->G * d->C * 8 > kMaxSmemBytes) return GSCAN_E_UNSUPPORTED;
+  Layout L = make_layout(*d, false);
+  if (pick_nb(*d, L.RA, L.RB, true, false) == 0) return GSCAN_E_UNSUPPORTED;
+  if (pick_nb(*d, L.RA, L.RB, false, d->V <= 32) == 0) return GSCAN_E_UNSUPPORTED;
+  return GSCAN_OK;
+}
+
+size_t gscan_workspace_floats(const gscan_dims* d) { return d ? make_layout(*d, true).total : 0; }
+size_t gscan_encode_workspace_floats(const gscan_dims* d) {
+  if (!d) return 0;
+  gscan_dims e = *d;
+  e.Tt = 1;
+  return make_layout(e, false).total;
+}
+size_t gscan_step_workspace_floats(const gscan_dims* d) {
+  if (!d) return 0;
+  gscan_dims e = *d;
+  e.Tt = 1;
+  return make_layout(e, false).total;
+}
+size_t gscan_greedy_workspace_floats(const gscan_dims* d) {
+  if (!d) return 0;
+  gscan_dims e = *d;
+  e.Tt = 1;
+  // + tables: XeTab [V][4H], Wout [V][4H], OutE [V][V], Wo_t [3H][Vp]
+  size_t extra = 2 * (size_t)d->V * 4 * d->H + (size_t)d->V * d->V + 3 * (size_t)d->H * pad4(d->V) + 64;
+  return make_layout(e, false).total + extra;
+}
+
+int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                  const float* situations, const int64_t* targets, const float* drop_cnn, const float* drop_enc,
+                  const float* drop_dec, float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream) {
+  TRY(check_common(d, P));
+  if (!commands || !cmd_len || !situations || !targets || !ws || !logp) return GSCAN_E_BADARG;
+  if (d->auxiliary_task && !aux_logp) return GSCAN_E_BADARG;
+  if (!aligned16(ws)) return GSCAN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Layout L = make_layout(*d, true);
+  if (ws_floats < L.total) return GSCAN_E_WORKSPACE;
+  const int B = d->B, Tt = d->Tt, M = d->G * d->G, H = d->H, V = d->V;
+  const long long* cmds = reinterpret_cast<const long long*>(commands);
+  const long long* tgts = reinterpret_cast<const long long*>(targets);
+
+  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, st));
+  TRY(pack_decoder_weights(*d, P, ws, L, st));
+  // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
+  {
+    long n = (long)B * Tt * H;
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
+                                                              4 * H, B, Tt, 1);
+    GSCAN_CHECK_LAUNCH();
+  }
+  float* U1 = ws + L.U + (size_t)B * 4 * H;
+  // input-gate pre-activations of every step at once: Xe = E . W_ih[:, :H]^T + b_ih + b_hh
+  TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, Tt * B, 4 * H, H, P[GSCAN_P_DEC_BIH],
+             P[GSCAN_P_DEC_BHH], 0, st));
+  DecFwdP p{};
+  fill_dec_fwd_common(*d, P, ws, L, p);
+  p.T = Tt;
+  p.KT = ws + L.KT; p.KV = ws + L.KV; p.cmd_len = cmd_len;
+  p.h_init = ws + L.h0; p.c_init = ws + L.h0;
+  p.Xe = ws + L.Xe;
+  p.U = ws + L.U; p.Cs = ws + L.Cs; p.gates = ws + L.gates; p.alpha = ws + L.alpha; p.beta = ws + L.beta;
+  p.Qp = ws + L.Qp; p.qT = ws + L.qT; p.qV = ws + L.qV; p.beta_sum = ws + L.beta_sum;
+  TRY(launch_dec_fwd(*d, p, false, st));
+  // output projection for all steps at once, then log-softmax
+  TRY(linear(U1, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre, H, Tt * B, H, 4 * H, nullptr, nullptr, 0, st));
+  {
+    size_t smem = (size_t)V * (H + 1) * sizeof(float);
+    if (smem > 48 * 1024) TRY(set_smem(out_logsoftmax_kernel, smem));
+    int blocks = min(ceil_div(Tt * B, 8), 8 * num_sms());
+    out_logsoftmax_kernel<<<blocks, 256, smem, st>>>(ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.logp, nullptr);
+    GSCAN_CHECK_LAUNCH();
+    TRYCUDA(cudaMemcpyAsync(logp, ws + L.logp, sizeof(float) * (size_t)B * Tt * V, cudaMemcpyDeviceToDevice, st));
+  }
+  if (d->auxiliary_task) {
+    row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(ws + L.beta_sum, M, B, ws + L.aux_logp);
+    GSCAN_CHECK_LAUNCH();
+    TRYCUDA(cudaMemcpyAsync(aux_logp, ws + L.aux_logp, sizeof(float) * (size_t)B * M, cudaMemcpyDeviceToDevice, st));
+  }
+  return GSCAN_OK;
+}
+
+int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                   const float* situations, const int64_t* targets, const float* drop_cnn, const float* drop_enc,
+                   const float* drop_dec, float* ws, size_t ws_floats, const float* d_logp, const float* d_aux_logp,
+                   float* const* G, void* stream) {
+  TRY(check_common(d, P));
+  if (!commands || !cmd_len || !situations || !targets || !ws || !d_logp || !G) return GSCAN_E_BADARG;
+  for (int i = 0; i < GSCAN_NUM_PARAMS; ++i) {
+    bool optional = (i == GSCAN_P_COND_W || i == GSCAN_P_COND_B) && !d->conditional_attention;
+    if (!optional && !G[i]) return GSCAN_E_BADARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Layout L = make_layout(*d, true);
+  if (ws_floats < L.total) return GSCAN_E_WORKSPACE;
+  const int B = d->B, Ti = d->Ti, Tt = d->Tt, M = d->G * d->G, D = 3 * d->F, H = d->H, E = d->E, V = d->V;
+  const int R = Tt * B;
+  const int sms = num_sms();
+  const long long* cmds = reinterpret_cast<const long long*>(commands);
+  const long long* tgts = reinterpret_cast<const long long*>(targets);
+  float* U0 = ws + L.U;
+  float* U1 = ws + L.U + (size_t)B * 4 * H;
+
+  // B1: log-softmax backward, hidden_to_output
+  {
+    int blocks = min(ceil_div(R, 8), 8 * sms);
+    logsoftmax_bwd_kernel<<<blocks, 256, 0, st>>>(d_logp, ws + L.logp, V, B, Tt, ws + L.dlogits);
+    GSCAN_CHECK_LAUNCH();
+  }
+  TRY(matmul_nn(ws + L.dlogits, V, P[GSCAN_P_H2O_W], H, ws + L.dpre, H, R, H, V, 0, st));
+  TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, st));
+  // B2: output_to_hidden
+  TRY(matmul_nn(ws + L.dpre, H, P[GSCAN_P_O2H_W], 4 * H, ws + L.dU, 4 * H, R, 4 * H, H, 0, st));
+  TRY(launch_grad_gemm(ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H, R, sms, st));
+  // B3: auxiliary head
+  const float* dbeta_aux = nullptr;
+  if (d->auxiliary_task && d_aux_logp) {
+    row_logsoftmax_bwd_kernel<<<ceil_div(B, 8), 256, 0, st>>>(d_aux_logp, ws + L.aux_logp, M, B, ws + L.dbeta_aux);
+    GSCAN_CHECK_LAUNCH();
+    dbeta_aux = ws + L.dbeta_aux;
+  }
+  // B4: reverse-time sweep
+  TRYCUDA(cudaMemsetAsync(ws + L.dvec, 0, sizeof(float) * 2 * H, st));
+  DecBwdP bp{};
+  bp.B = B; bp.T = Tt; bp.Ti = Ti; bp.M = M; bp.H = H; bp.cond = d->conditional_attention;
+  bp.W_ih = P[GSCAN_P_DEC_WIH]; bp.W_hh = P[GSCAN_P_DEC_WHH]; bp.W_qV = P[GSCAN_P_VIS_QUERY_W];
+  bp.W_c = P[GSCAN_P_COND_W]; bp.W_qT = P[GSCAN_P_TXT_QUERY_W];
+  bp.vT = P[GSCAN_P_TXT_ENERGY_W]; bp.vV = P[GSCAN_P_VIS_ENERGY_W];
+  bp.KT = ws + L.KT; bp.KV = ws + L.KV; bp.cmd_len = cmd_len;
+  bp.Cs = ws + L.Cs; bp.gates = ws + L.gates; bp.alpha = ws + L.alpha; bp.beta = ws + L.beta;
+  bp.Qp = ws + L.Qp; bp.qT = ws + L.qT; bp.qV = ws + L.qV;
+  bp.dU = ws + L.dU; bp.dbeta_aux = dbeta_aux;
+  bp.dgates = ws + L.dgates; bp.dd = ws + L.dd; bp.dqV = ws + L.dqV; bp.dqT = ws + L.dqT;
+  bp.dKT = ws + L.dKT; bp.dKV = ws + L.dKV; bp.dh0 = ws + L.dh0;
+  bp.dvT = ws + L.dvec; bp.dvV = ws + L.dvec + H;
+  TRY(launch_dec_bwd(*d, bp, st));
+  TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
+  TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
+  // B5: decoder weight gradients as batched "TN" products over all steps
+  const float* Hprev = U0 + H;       // rows t*B+b hold h_{t-1}
+  TRY(launch_grad_gemm(ws + L.dgates, 4 * H, U1, 4 * H, G[GSCAN_P_DEC_WIH], 3 * H, 4 * H, H, R, sms, st));
+  TRY(launch_grad_gemm(ws + L.dgates, 4 * H, U1 + 2 * H, 4 * H, G[GSCAN_P_DEC_WIH] + H, 3 * H, 4 * H, 2 * H, R, sms, st));
+  TRY(launch_grad_gemm(ws + L.dgates, 4 * H, Hprev, 4 * H, G[GSCAN_P_DEC_WHH], H, 4 * H, H, R, sms, st));
+  TRY(launch_colsum(ws + L.dgates, 4 * H, R, 4 * H, G[GSCAN_P_DEC_BIH], st));
+  TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_DEC_BHH], G[GSCAN_P_DEC_BIH], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+  TRY(launch_grad_gemm(ws + L.dqT, H, Hprev, 4 * H, G[GSCAN_P_TXT_QUERY_W], H, H, H, R, sms, st));
+  TRY(launch_grad_gemm(ws + L.dqV, H, ws + L.Qp, H, G[GSCAN_P_VIS_QUERY_W], H, H, H, R, sms, st));
+  if (d->conditional_attention) {
+    TRY(launch_grad_gemm(ws + L.dd, H, Hprev, 4 * H, G[GSCAN_P_COND_W], 2 * H, H, H, R, sms, st));
+    TRY(launch_grad_gemm(ws + L.dd, H, U1 + 2 * H, 4 * H, G[GSCAN_P_COND_W] + H, 2 * H, H, H, R, sms, st));
+    TRY(launch_colsum(ws + L.dd, H, R, H, G[GSCAN_P_COND_B], st));
+  }
+  // decoder embedding: dE = dU[:, :H] + dgates . W_ih[:, :H], then scatter by token
+  TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.dU, 4 * H, R, H, 4 * H, 1, st));
+  {
+    TRYCUDA(cudaMemsetAsync(G[GSCAN_P_DEC_EMB], 0, sizeof(float) * (size_t)V * H, st));
+    int use_smem = ((size_t)V * H * sizeof(float) <= 48 * 1024);
+    int rpb = 128;
+    embed_bwd_kernel<<<ceil_div(R, rpb), 256, use_smem ? (size_t)V * H * sizeof(float) : 0, st>>>(
+        tgts, Tt, ws + L.dU, 4 * H, drop_dec, G[GSCAN_P_DEC_EMB], H, V, d->pad_idx_out, B, Tt, 1, rpb, use_smem);
+    GSCAN_CHECK_LAUNCH();
+  }
+  // B6: visual keys -> CNN
+  TRY(launch_grad_gemm(ws + L.dKV, H, ws + L.feat, D, G[GSCAN_P_VIS_KEY_W], D, H, D, B * M, sms, st));
+  TRY(matmul_nn(ws + L.dKV, H, P[GSCAN_P_VIS_KEY_W], D, ws + L.dfeat, D, B * M, D, H, 0, st));
+  {
+    long n = (long)B * M * D;
+    cnn_dact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws + L.dfeat, ws + L.feat, drop_cnn, ws + L.dconv, n);
+    GSCAN_CHECK_LAUNCH();
+    CnnShape cs{B, d->G, d->C, d->F, d->K3};
+    TRYCUDA(cudaMemsetAsync(ws + L.dWt_cnn, 0, sizeof(float) * cs.wtotal(), st));
+    size_t smem = (size_t)B * 8;
+    if (smem > 48 * 1024) TRY(set_smem(cnn_wgrad_kernel, smem));
+    cnn_wgrad_kernel<<<M * d->C, 256, smem, st>>>(cs, situations, ws + L.dconv, ws + L.dWt_cnn);
+    GSCAN_CHECK_LAUNCH();
+    cnn_relayout_kernel<<<ceil_div(cs.wtotal(), 256), 256, 0, st>>>(cs, G[GSCAN_P_CONV1_W], G[GSCAN_P_CONV2_W],
+                                                                   G[GSCAN_P_CONV3_W], ws + L.dWt_cnn, 0);
+    GSCAN_CHECK_LAUNCH();
+    TRY(launch_colsum(ws + L.dconv, D, B * M, d->F, G[GSCAN_P_CONV1_B], st));
+    TRY(launch_colsum(ws + L.dconv + d->F, D, B * M, d->F, G[GSCAN_P_CONV2_B], st));
+    TRY(launch_colsum(ws + L.dconv + 2 * d->F, D, B * M, d->F, G[GSCAN_P_CONV3_B], st));
+  }
+  // B7: textual keys and initial state
+  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, st));
+  TRY(matmul_nn(ws + L.dKT, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.denc_out, H, Ti * B, H, H, 0, st));
+  TRY(launch_tanh_bwd(ws + L.dh0, ws + L.h0, ws + L.dpre0, (long)B * H, st));
+  TRY(launch_grad_gemm(ws + L.dpre0, H, ws + L.h_enc, H, G[GSCAN_P_E2D_W], H, H, H, B, sms, st));
+  TRY(launch_colsum(ws + L.dpre0, H, B, H, G[GSCAN_P_E2D_B], st));
+  TRY(matmul_nn(ws + L.dpre0, H, P[GSCAN_P_E2D_W], H, ws + L.dh_enc, H, B, H, H, 0, st));
+  // B8: encoder BPTT
+  EncP ep{};
+  ep.B = B; ep.Ti = Ti; ep.H = H;
+  ep.W_hh[0] = P[GSCAN_P_ENC_WHH]; ep.W_hh[1] = P[GSCAN_P_ENC_WHH_R];
+  for (int i = 0; i < 2; ++i) {
+    ep.enc_h[i] = ws + L.enc_h[i];
+    ep.enc_c[i] = ws + L.enc_c[i];
+    ep.enc_g[i] = ws + L.enc_g[i];
+    ep.dga[i] = ws + L.dga[i];
+    ep.hprev[i] = ws + L.hprev[i];
+  }
+  ep.len = cmd_len;
+  ep.denc_out = ws + L.denc_out;
+  ep.dh_enc = ws + L.dh_enc;
+  TRY(launch_enc(*d, ep, true, st));
+  const int RE = B * Ti;
+  const int wih[2] = {GSCAN_P_ENC_WIH, GSCAN_P_ENC_WIH_R}, whh[2] = {GSCAN_P_ENC_WHH, GSCAN_P_ENC_WHH_R};
+  const int bih[2] = {GSCAN_P_ENC_BIH, GSCAN_P_ENC_BIH_R}, bhh[2] = {GSCAN_P_ENC_BHH, GSCAN_P_ENC_BHH_R};
+  for (int i = 0; i < 2; ++i) {
+    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.enc_x, E, G[wih[i]], E, 4 * H, E, RE, sms, st));
+    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.hprev[i], H, G[whh[i]], H, 4 * H, H, RE, sms, st));
+    TRY(launch_colsum(ws + L.dga[i], 4 * H, RE, 4 * H, G[bih[i]], st));
+    TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
+    TRY(matmul_nn(ws + L.dga[i], 4 * H, P[wih[i]], E, ws + L.denc_x, E, RE, E, 4 * H, i, st));
+  }
+  {
+    TRYCUDA(cudaMemsetAsync(G[GSCAN_P_ENC_EMB], 0, sizeof(float) * (size_t)d->Vi * E, st));
+    int use_smem = ((size_t)d->Vi * E * sizeof(float) <= 48 * 1024);
+    int rpb = 64;
+    embed_bwd_kernel<<<ceil_div(RE, rpb), 256, use_smem ? (size_t)d->Vi * E * sizeof(float) : 0, st>>>(
+        cmds, d->Ti_stride, ws + L.denc_x, E, drop_enc, G[GSCAN_P_ENC_EMB], E, d->Vi, d->pad_idx_in, B, Ti, 0, rpb,
+        use_smem);
+    GSCAN_CHECK_LAUNCH();
+  }
+  return GSCAN_OK;
+}
+
+int gscan_encode(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                 const float* situations, const float* drop_cnn, const float* drop_enc, float* ws, size_t ws_floats,
+                 float* feat, float* enc_out, float* hidden, void* stream) {
+  TRY(check_common(d, P));
+  if (!commands || !cmd_len || !situations || !ws || !feat || !enc_out || !hidden) return GSCAN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  gscan_dims e = *d;
+  e.Tt = 1;
+  Layout L = make_layout(e, false);
+  if (ws_floats < L.total) return GSCAN_E_WORKSPACE;
+  const size_t B = d->B, Ti = d->Ti, M = (size_t)d->G * d->G, D = 3 * (size_t)d->F, H = d->H;
+  TRY(run_encoder_side(e, P, reinterpret_cast<const long long*>(commands), cmd_len, situations, drop_cnn, drop_enc,
+                       ws, L, false, st));
+  TRYCUDA(cudaMemcpyAsync(feat, ws + L.feat, sizeof(float) * B * M * D, cudaMemcpyDeviceToDevice, st));
+  TRYCUDA(cudaMemcpyAsync(enc_out, ws + L.enc_out, sizeof(float) * Ti * B * H, cudaMemcpyDeviceToDevice, st));
+  TRYCUDA(cudaMemcpyAsync(hidden, ws + L.h_enc, sizeof(float) * B * H, cudaMemcpyDeviceToDevice, st));
+  return GSCAN_OK;
+}
+
+int gscan_decoder_step(const gscan_dims* d, const float* const* P, const int64_t* tokens, const float* h_in,
+                       const float* c_in, const float* keys_text, const int32_t* cmd_len, const float* keys_vis,
+                       const float* drop_dec, float* ws, size_t ws_floats, float* logits, float* h_out, float* c_out,
+                       float* alpha, float* beta, void* stream) {
+  TRY(check_common(d, P));
+  if (!tokens || !h_in || !c_in || !keys_text || !cmd_len || !keys_vis || !ws || !logits || !h_out || !c_out)
+    return GSCAN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  gscan_dims e = *d;
+  e.Tt = 1;
+  Layout L = make_layout(e, false);
+  if (ws_floats < L.total) return GSCAN_E_WORKSPACE;
+  const int B = d->B, H = d->H, V = d->V;
+  TRY(pack_decoder_weights(e, P, ws, L, st));
+  {
+    long n = (long)B * H;
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long*>(tokens), 1,
+                                                              P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U, 4 * H, B, 1, 1);
+    GSCAN_CHECK_LAUNCH();
+  }
+  float* U1 = ws + L.U + (size_t)B * 4 * H;
+  TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, B, 4 * H, H, P[GSCAN_P_DEC_BIH],
+             P[GSCAN_P_DEC_BHH], 0, st));
+  DecFwdP p{};
+  fill_dec_fwd_common(e, P, ws, L, p);
+  p.T = 1;
+  p.KT = keys_text; p.KV = keys_vis; p.cmd_len = cmd_len;
+  p.h_init = h_in; p.c_init = c_in;
+  p.Xe = ws + L.Xe;
+  p.U = ws + L.U;
+  p.alpha = alpha; p.beta = beta;
+  p.h_out = h_out; p.c_out = c_out;
+  TRY(launch_dec_fwd(e, p, false, st));
+  TRY(linear(U1, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre, H, B, H, 4 * H, nullptr, nullptr, 0, st));
+  size_t smem = (size_t)V * (H + 1) * sizeof(float);
+  if (smem > 48 * 1024) TRY(set_smem(out_logsoftmax_kernel, smem));
+  out_logsoftmax_kernel<<<min(ceil_div(B, 8), 8 * num_sms()), 256, smem, st>>>(ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, 1,
+                                                                               nullptr, logits);
+  GSCAN_CHECK_LAUNCH();
+  return GSCAN_OK;
+}
+
+int gscan_greedy_decode(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                        const float* situations, int32_t max_decoding_steps, int32_t sos, int32_t eos, float* ws,
+                        size_t ws_floats, int64_t* out_tokens, int32_t* out_len, int32_t* out_steps, float* beta_sum,
+                        float* aux_logp, float* alphas, float* betas, void* stream) {
+  TRY(check_common(d, P));
+  if (!commands || !cmd_len || !situations || !ws || !out_tokens || !out_len || !out_steps || !beta_sum)
+    return GSCAN_E_BADARG;
+  if (max_decoding_steps < 0 || d->V > 32) return GSCAN_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  gscan_dims e = *d;
+  e.Tt = 1;
+  Layout L = make_layout(e, false);
+  if (ws_floats < gscan_greedy_workspace_floats(d)) return GSCAN_E_WORKSPACE;
+  const int B = d->B, M = d->G * d->G, H = d->H, V = d->V, Vp = pad4(V);
+  const int T = max_decoding_steps + 1;
+  float* XeTab = ws + L.total;
+  float* Wout = XeTab + pad4(V * 4 * H);
+  float* OutE = Wout + pad4(V * 4 * H);
+  float* Wo_t = OutE + pad4(V * V);
+  TRY(run_encoder_side(e, P, reinterpret_cast<const long long*>(commands), cmd_len, situations, nullptr, nullptr, ws,
+                       L, true, st));
+  TRY(pack_decoder_weights(e, P, ws, L, st));
+  // eval-mode tables: the embedding-dependent parts of the gates and of the logits have only V rows
+  TRY(linear(P[GSCAN_P_DEC_EMB], H, P[GSCAN_P_DEC_WIH], 3 * H, XeTab, 4 * H, V, 4 * H, H, P[GSCAN_P_DEC_BIH],
+             P[GSCAN_P_DEC_BHH], 0, st));
+  TRY(matmul_nn(P[GSCAN_P_H2O_W], H, P[GSCAN_P_O2H_W], 4 * H, Wout, 4 * H, V, 4 * H, H, 0, st));
+  TRY(linear(P[GSCAN_P_DEC_EMB], H, Wout, 4 * H, OutE, V, V, V, H, nullptr, nullptr, 0, st));
+  TRYCUDA(cudaMemsetAsync(Wo_t, 0, sizeof(float) * 3 * H * Vp, st));
+  {
+    PackTable tab;
+    tab.n = 1;
+    tab.d[0] = PackDesc{Wout, 4 * H, H, Wo_t, Vp, 0, V, 3 * H};
+    TRY(launch_pack(tab, st));
+  }
+  {
+    long n = (long)B * T;
+    fill_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(out_tokens), n, -1);
+    GSCAN_CHECK_LAUNCH();
+  }
+  DecFwdP p{};
+  fill_dec_fwd_common(e, P, ws, L, p);
+  p.T = T;
+  p.KT = ws + L.KT; p.KV = ws + L.KV; p.cmd_len = cmd_len;
+  p.h_init = ws + L.h0; p.c_init = ws + L.h0;
+  p.beta_sum = beta_sum;
+  p.XeTab = XeTab; p.OutE = OutE; p.Wo_t = Wo_t; p.Vp = Vp; p.sos = sos; p.eos = eos;
+  p.out_tokens = reinterpret_cast<long long*>(out_tokens);
+  p.out_len = out_len; p.out_steps = out_steps;
+  p.g_alphas = alphas; p.g_betas = betas;
+  TRY(launch_dec_fwd(e, p, true, st));
+  if (aux_logp) {
+    row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(beta_sum, M, B, aux_logp);
+    GSCAN_CHECK_LAUNCH();
+  }
+  return GSCAN_OK;
+}
+
+int gscan_nll_forward(const float* logp, const int64_t* targets, int32_t B, int32_t Tt, int32_t V, int32_t pad_idx,
+                      int32_t shift, float* loss_out, void* stream) {
+  if (!logp || !targets || !loss_out || B < 1 || Tt < 1 || V < 1 || shift < 0) return GSCAN_E_BADARG;
+  nll_forward_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logp, reinterpret_cast<const long long*>(targets), B, Tt, V,
+                                                          pad_idx, shift, loss_out);
+  GSCAN_CHECK_LAUNCH();
+  return GSCAN_OK;
+}
+
+int gscan_nll_backward(const int64_t* targets, int32_t B, int32_t Tt, int32_t V, int32_t pad_idx, int32_t shift,
+                       const float* loss_out, const float* d_loss, float* d_logp, void* stream) {
+  if (!targets || !loss_out || !d_loss || !d_logp || shift < 0) return GSCAN_E_BADARG;
+  long n = (long)B * Tt * V;
+  nll_backward_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(targets), B, Tt, V, pad_idx, shift, loss_out, d_loss, d_logp);
+  GSCAN_CHECK_LAUNCH();
+  return GSCAN_OK;
+}
+
+int gscan_metrics(const float* logp, const int64_t* targets, int32_t B, int32_t Tt, int32_t V, int32_t pad_idx,
+                  int32_t* counts, void* stream) {
+  if (!logp || !targets || !counts) return GSCAN_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  TRYCUDA(cudaMemsetAsync(counts, 0, 3 * sizeof(int32_t), st));
+  metrics_kernel<<<ceil_div(B, 8), 256, 0, st>>>(logp, reinterpret_cast<const long long*>(targets), B, Tt, V, pad_idx,
+                                                 counts);
+  GSCAN_CHECK_LAUNCH();
+  return GSCAN_OK;
+}
+
+int gscan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                    float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return GSCAN_E_BADARG;
+  if (n == 0) return GSCAN_OK;
+  float bc1 = 1.f - powf(beta1, (float)step);
+  float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr,
+                                                                            beta1, beta2, eps, bc1, bc2s, grad_scale);
+  GSCAN_CHECK_LAUNCH();
+  return GSCAN_OK;
+}
+
+int gscan_sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs, float* C,
+                int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, int32_t act, int32_t accumulate,
+                void* stream) {
+  if (!A || !B || !C || M < 0 || N < 0 || K < 0) return GSCAN_E_BADARG;
+  return launch_sgemm(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, bias, nullptr, act, accumulate, 1,
+                      (cudaStream_t)stream);
+}
+
+int gscan_cnn_forward(const gscan_dims* d, const float* const* P, const float* situations, const float* drop_cnn,
+                      float* ws, size_t ws_floats, float* feat, void* stream) {
+  if (!d || !P || !situations || !ws || !feat) return GSCAN_E_BADARG;
+  CnnShape cs{d->B, d->G, d->C, d->F, d->K3};
+  if (ws_floats < (size_t)cs.wtotal()) return GSCAN_E_WORKSPACE;
+  return run_cnn_forward(*d, P, situations, drop_cnn, ws, feat, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,325 @@
+"""Host-side glue between torch tensors and the C ABI (include/gscan_b200.h).
+
+torch owns memory, streams and autograd bookkeeping; every arithmetic operation of the path runs
+in libgscan_b200.so.  The ``autograd.Function`` classes here play the role autograd's recorded
+graph plays in the reference: ``ModelForward`` saves the workspace written by ``gscan_forward``
+and hands it to ``gscan_backward``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Dims, ParamArray
+
+# launches issued by the library since import, for bench.py's "gpu_launches" claim
+_call_counts = {"forward": 0, "backward": 0, "greedy": 0, "other": 0}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("multimodal_seq2seq_gscan_b200 runs only on CUDA tensors (sm_100a kernels); "
+                               "there is no CPU fallback. Move the model and its inputs to a CUDA device.")
+
+
+def _param_array(tensors: Sequence[Optional[torch.Tensor]]) -> ParamArray:
+    arr = ParamArray()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def lengths_to_device(lengths, device) -> torch.Tensor:
+    """The reference passes lengths as host lists / numpy float64 arrays (gSCAN_dataset.py:198-199);
+    the kernels want int32 on the device.  No sync: the copy is stream-ordered."""
+    if isinstance(lengths, torch.Tensor):
+        return lengths.to(device=device, dtype=torch.int32)
+    arr = np.ascontiguousarray(np.asarray(lengths).astype(np.int32))
+    return torch.from_numpy(arr).to(device, non_blocking=True)
+
+
+def max_length(lengths) -> int:
+    if isinstance(lengths, torch.Tensor):
+        return int(lengths.max().item())
+    return int(np.max(np.asarray(lengths)))
+
+
+def make_dims(cfg: dict, B: int, Ti: int, Tt: int, Ti_stride: int) -> Dims:
+    d = Dims()
+    d.B, d.Ti, d.Tt, d.Ti_stride = B, Ti, Tt, Ti_stride
+    for k in ("G", "C", "F", "K3", "E", "H", "Vi", "V", "conditional_attention", "auxiliary_task", "pad_idx_in",
+              "pad_idx_out"):
+        setattr(d, k, int(cfg[k]))
+    return d
+
+
+def _dropout_mask(shape, p: float, device, generator=None) -> Optional[torch.Tensor]:
+    if p <= 0.0:
+        return None
+    mask = torch.empty(shape, dtype=torch.float32, device=device)
+    mask.bernoulli_(1.0 - p, generator=generator)
+    return mask.mul_(1.0 / (1.0 - p))
+
+
+class ModelForward(torch.autograd.Function):
+    """(logp [B,Tt,V], aux_logp [B,M]) = gscan_forward(...); backward = gscan_backward(...)."""
+
+    @staticmethod
+    def forward(ctx, cfg, commands, cmd_len_dev, Ti, situations, targets, masks, *params):
+        lib = _lib.load()
+        _require_cuda(commands, situations, targets, *[p for p in params if p is not None])
+        dev = situations.device
+        B, Tt = targets.shape
+        commands = commands.contiguous()
+        situations = situations.contiguous().float()
+        targets = targets.contiguous()
+        dims = make_dims(cfg, B, Ti, Tt, commands.shape[1])
+        _lib.check(lib.gscan_check_dims(dims), "gscan_check_dims")
+        M = dims.G * dims.G
+        n_ws = lib.gscan_workspace_floats(dims)
+        ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
+        logp = torch.empty(B, Tt, dims.V, dtype=torch.float32, device=dev)
+        aux = torch.empty(B, M, dtype=torch.float32, device=dev) if dims.auxiliary_task else None
+        parr = _param_array([None if p is None else p.detach() for p in params])
+        drop_cnn, drop_enc, drop_dec = masks
+        rc = lib.gscan_forward(dims, parr, _ptr(commands), _ptr(cmd_len_dev), _ptr(situations), _ptr(targets),
+                               _ptr(drop_cnn), _ptr(drop_enc), _ptr(drop_dec), _ptr(ws), n_ws, _ptr(logp), _ptr(aux),
+                               _stream(dev))
+        _lib.check(rc, "gscan_forward")
+        _call_counts["forward"] += 1
+        ctx.dims = dims
+        ctx.n_ws = n_ws
+        ctx.param_shapes = [None if p is None else p.shape for p in params]
+        ctx.save_for_backward(commands, cmd_len_dev, situations, targets, ws, *[m for m in masks if m is not None],
+                              *[p for p in params if p is not None])
+        ctx.mask_present = [m is not None for m in masks]
+        ctx.param_present = [p is not None for p in params]
+        if aux is None:
+            aux = torch.zeros(1, device=dev)
+            ctx.mark_non_differentiable(aux)
+        return logp, aux
+
+    @staticmethod
+    def backward(ctx, d_logp, d_aux):
+        lib = _lib.load()
+        saved = list(ctx.saved_tensors)
+        commands, cmd_len_dev, situations, targets, ws = saved[:5]
+        rest = saved[5:]
+        masks = []
+        for present in ctx.mask_present:
+            masks.append(rest.pop(0) if present else None)
+        params = []
+        for present in ctx.param_present:
+            params.append(rest.pop(0) if present else None)
+        dims = ctx.dims
+        dev = situations.device
+        if d_logp is None:
+            d_logp = torch.zeros(dims.B, dims.Tt, dims.V, dtype=torch.float32, device=dev)
+        d_logp = d_logp.contiguous().float()
+        if not dims.auxiliary_task:
+            d_aux = None
+        elif d_aux is not None:
+            d_aux = d_aux.contiguous().float()
+        # one flat fp32 gradient buffer in model.parameters() order; the per-parameter gradients
+        # returned to autograd are views into it (this is also the data-parallel all-reduce buffer)
+        sizes = [0 if s is None else int(np.prod(s)) for s in ctx.param_shapes]
+        offsets = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])])
+        flat = torch.empty(int(offsets[-1]), dtype=torch.float32, device=dev)
+        views = [None if s is None else flat[int(o):int(o) + n].view(s)
+                 for s, o, n in zip(ctx.param_shapes, offsets[:-1], sizes)]
+        rc = lib.gscan_backward(dims, _param_array(params), _ptr(commands), _ptr(cmd_len_dev), _ptr(situations),
+                                _ptr(targets), _ptr(masks[0]), _ptr(masks[1]), _ptr(masks[2]), _ptr(ws), ctx.n_ws,
+                                _ptr(d_logp), _ptr(d_aux), _param_array(views), _stream(dev))
+        _lib.check(rc, "gscan_backward")
+        _call_counts["backward"] += 1
+        return (None, None, None, None, None, None, None, *views)
+
+
+class NLLLoss(torch.autograd.Function):
+    """Mean NLL over non-ignored targets shifted by ``shift`` (gscan_nll_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, logp, targets, pad_idx, shift):
+        lib = _lib.load()
+        _require_cuda(logp, targets)
+        logp = logp.contiguous().float()
+        targets = targets.contiguous()
+        B, T, V = logp.shape
+        out = torch.empty(2, dtype=torch.float32, device=logp.device)
+        _lib.check(lib.gscan_nll_forward(_ptr(logp), _ptr(targets), B, T, V, int(pad_idx), int(shift), _ptr(out),
+                                         _stream(logp.device)), "gscan_nll_forward")
+        _call_counts["other"] += 1
+        ctx.save_for_backward(targets, out)
+        ctx.meta = (B, T, V, int(pad_idx), int(shift))
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, d_loss):
+        lib = _lib.load()
+        targets, out = ctx.saved_tensors
+        B, T, V, pad_idx, shift = ctx.meta
+        d_loss = d_loss.contiguous().float().reshape(1)
+        d_logp = torch.empty(B, T, V, dtype=torch.float32, device=out.device)
+        _lib.check(lib.gscan_nll_backward(_ptr(targets), B, T, V, pad_idx, shift, _ptr(out), _ptr(d_loss), _ptr(d_logp),
+                                          _stream(out.device)), "gscan_nll_backward")
+        _call_counts["other"] += 1
+        return d_logp, None, None, None
+
+
+def metrics_counts(logp: torch.Tensor, targets: torch.Tensor, pad_idx: int) -> torch.Tensor:
+    """int32[3] on the device: matching tokens, non-pad tokens, exactly matching sequences."""
+    lib = _lib.load()
+    _require_cuda(logp, targets)
+    logp = logp.detach().contiguous().float()
+    targets = targets.contiguous()
+    B, T, V = logp.shape
+    counts = torch.empty(3, dtype=torch.int32, device=logp.device)
+    _lib.check(lib.gscan_metrics(_ptr(logp), _ptr(targets), B, T, V, int(pad_idx), _ptr(counts),
+                                 _stream(logp.device)), "gscan_metrics")
+    _call_counts["other"] += 1
+    return counts
+
+
+def sgemm_nt(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = 0) -> torch.Tensor:
+    """y = act(x @ weight.T + bias) on the library's GEMM (no autograd)."""
+    lib = _lib.load()
+    _require_cuda(x, weight)
+    shape = x.shape
+    x2 = x.detach().reshape(-1, shape[-1]).contiguous().float()
+    w = weight.detach().contiguous()
+    M, K = x2.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    _lib.check(lib.gscan_sgemm(_ptr(x2), K, 1, _ptr(w), 1, K, _ptr(y), N, M, N, K,
+                               None if bias is None else bias.detach().data_ptr(), act, 0, _stream(x.device)),
+               "gscan_sgemm")
+    _call_counts["other"] += 1
+    return y.view(*shape[:-1], N)
+
+
+def encode(cfg, params, commands, lengths, situations, masks=(None, None)):
+    lib = _lib.load()
+    _require_cuda(commands, situations)
+    dev = situations.device
+    commands = commands.contiguous()
+    situations = situations.contiguous().float()
+    B = commands.shape[0]
+    Ti = max_length(lengths)
+    cmd_len = lengths_to_device(lengths, dev)
+    dims = make_dims(cfg, B, Ti, 1, commands.shape[1])
+    _lib.check(lib.gscan_check_dims(dims), "gscan_check_dims")
+    n_ws = lib.gscan_encode_workspace_floats(dims)
+    ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
+    M, D = dims.G * dims.G, 3 * dims.F
+    feat = torch.empty(B, M, D, dtype=torch.float32, device=dev)
+    enc_out = torch.empty(Ti, B, dims.H, dtype=torch.float32, device=dev)
+    hidden = torch.empty(B, dims.H, dtype=torch.float32, device=dev)
+    rc = lib.gscan_encode(dims, _param_array([None if p is None else p.detach() for p in params]), _ptr(commands),
+                          _ptr(cmd_len), _ptr(situations), _ptr(masks[0]), _ptr(masks[1]), _ptr(ws), n_ws, _ptr(feat),
+                          _ptr(enc_out), _ptr(hidden), _stream(dev))
+    _lib.check(rc, "gscan_encode")
+    _call_counts["other"] += 1
+    return feat, enc_out, hidden
+
+
+def decoder_step(cfg, params, tokens, h, c, keys_text, lengths, keys_vis, drop_dec=None):
+    lib = _lib.load()
+    _require_cuda(tokens, h, c, keys_text, keys_vis)
+    dev = h.device
+    tokens = tokens.contiguous()
+    h2 = h.detach().reshape(-1, h.shape[-1]).contiguous().float()
+    c2 = c.detach().reshape(-1, c.shape[-1]).contiguous().float()
+    keys_text = keys_text.detach().contiguous().float()
+    keys_vis = keys_vis.detach().contiguous().float()
+    Ti, B, H = keys_text.shape
+    cmd_len = lengths_to_device(lengths, dev)
+    dims = make_dims(cfg, B, Ti, 1, Ti)
+    _lib.check(lib.gscan_check_dims(dims), "gscan_check_dims")
+    n_ws = lib.gscan_step_workspace_floats(dims)
+    ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
+    M = dims.G * dims.G
+    logits = torch.empty(B, dims.V, dtype=torch.float32, device=dev)
+    h_out = torch.empty(B, H, dtype=torch.float32, device=dev)
+    c_out = torch.empty(B, H, dtype=torch.float32, device=dev)
+    alpha = torch.empty(B, Ti, dtype=torch.float32, device=dev)
+    beta = torch.empty(B, M, dtype=torch.float32, device=dev)
+    rc = lib.gscan_decoder_step(dims, _param_array([None if p is None else p.detach() for p in params]), _ptr(tokens),
+                                _ptr(h2), _ptr(c2), _ptr(keys_text), _ptr(cmd_len), _ptr(keys_vis), _ptr(drop_dec),
+                                _ptr(ws), n_ws, _ptr(logits), _ptr(h_out), _ptr(c_out), _ptr(alpha), _ptr(beta),
+                                _stream(dev))
+    _lib.check(rc, "gscan_decoder_step")
+    _call_counts["other"] += 1
+    return logits, h_out, c_out, alpha, beta
+
+
+def greedy_decode(cfg, params, commands, lengths, situations, max_decoding_steps, sos_idx, eos_idx,
+                  return_attention=False, want_aux=False):
+    lib = _lib.load()
+    _require_cuda(commands, situations)
+    dev = situations.device
+    commands = commands.contiguous()
+    situations = situations.contiguous().float()
+    B = commands.shape[0]
+    Ti = max_length(lengths)
+    cmd_len = lengths_to_device(lengths, dev)
+    dims = make_dims(cfg, B, Ti, 1, commands.shape[1])
+    _lib.check(lib.gscan_check_dims(dims), "gscan_check_dims")
+    n_ws = lib.gscan_greedy_workspace_floats(dims)
+    ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
+    T = int(max_decoding_steps) + 1
+    M = dims.G * dims.G
+    tokens = torch.empty(B, T, dtype=torch.int64, device=dev)
+    out_len = torch.empty(B, dtype=torch.int32, device=dev)
+    out_steps = torch.empty(B, dtype=torch.int32, device=dev)
+    beta_sum = torch.empty(B, M, dtype=torch.float32, device=dev)
+    aux = torch.empty(B, M, dtype=torch.float32, device=dev) if want_aux else None
+    alphas = torch.zeros(B, T, Ti, dtype=torch.float32, device=dev) if return_attention else None
+    betas = torch.zeros(B, T, M, dtype=torch.float32, device=dev) if return_attention else None
+    rc = lib.gscan_greedy_decode(dims, _param_array([None if p is None else p.detach() for p in params]),
+                                 _ptr(commands), _ptr(cmd_len), _ptr(situations), int(max_decoding_steps), int(sos_idx),
+                                 int(eos_idx), _ptr(ws), n_ws, _ptr(tokens), _ptr(out_len), _ptr(out_steps),
+                                 _ptr(beta_sum), _ptr(aux), _ptr(alphas), _ptr(betas), _stream(dev))
+    _lib.check(rc, "gscan_greedy_decode")
+    _call_counts["greedy"] += 1
+    return {"tokens": tokens, "lengths": out_len, "steps": out_steps, "beta_sum": beta_sum, "aux_logp": aux,
+            "attention_weights_commands": alphas, "attention_weights_situations": betas}
+
+
+def cnn_forward(cfg, params, situations, drop_cnn=None):
+    lib = _lib.load()
+    _require_cuda(situations)
+    dev = situations.device
+    situations = situations.contiguous().float()
+    B = situations.shape[0]
+    dims = make_dims(cfg, B, 1, 1, 1)
+    M, D = dims.G * dims.G, 3 * dims.F
+    n_ws = dims.C * dims.F * (1 + 25 + dims.K3 * dims.K3) + 16
+    ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
+    feat = torch.empty(B, M, D, dtype=torch.float32, device=dev)
+    rc = lib.gscan_cnn_forward(dims, _param_array([None if p is None else p.detach() for p in params]),
+                               _ptr(situations), _ptr(drop_cnn), _ptr(ws), n_ws, _ptr(feat), _stream(dev))
+    _lib.check(rc, "gscan_cnn_forward")
+    _call_counts["other"] += 1
+    return feat
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    lib = _lib.load()
+    _require_cuda(param, grad, exp_avg, exp_avg_sq)
+    n = param.numel()
+    _lib.check(lib.gscan_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, float(lr),
+                                   float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
+                                   _stream(param.device)), "gscan_adam_step")
+    _call_counts["other"] += 1

@@ -1,0 +1,339 @@
+"""Parity of the sm_100a kernels (through the drop-in Model -> C ABI) against the CPU oracle and the
+reference's golden vectors.  Tolerances: the north star asks for fp32 agreement within 1e-4
+relative; the reference's own fp32-vs-fp64 noise is ~5e-7 on log-probs and ~4e-6 rel-L2 on
+gradients, so we require:
+    log-probs     max-abs <= 2e-5     loss  rel <= 1e-5     gradients  rel-L2 <= 1e-4
+Greedy sequences, lengths and exact-match must be identical."""
+import numpy as np
+import pytest
+import torch
+
+import multimodal_seq2seq_gscan_b200 as pkg
+from multimodal_seq2seq_gscan_b200 import ops
+from oracle import gscan_oracle as O
+from tests.golden_util import CASE_NAMES, load_case
+from tests.gpu_util import DEV, build_model, oracle_run, rel_l2, to_dev
+
+pytestmark = pytest.mark.gpu
+
+LOGP_ATOL = 2e-5
+GRAD_RTOL = 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (128, 64, 16), (129, 65, 17), (300, 400, 100), (1000, 9, 100),
+                                   (9, 100, 2000)])
+def test_sgemm_forms(M, N, K):
+    lib = pkg.load()
+    g = torch.Generator().manual_seed(M * 1000 + N * 10 + K)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64)
+    Bm = torch.randn(K, N, generator=g, dtype=torch.float64)
+    bias = torch.randn(N, generator=g, dtype=torch.float64)
+    ref = A @ Bm
+    Ad, Bd = A.float().to(DEV), Bm.float().to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(a, a_rs, a_cs, b, b_rs, b_cs, bias_t=None, act=0, acc=0, C=None):
+        C = torch.zeros(M, N, device=DEV) if C is None else C
+        rc = lib.gscan_sgemm(a.data_ptr(), a_rs, a_cs, b.data_ptr(), b_rs, b_cs, C.data_ptr(), N, M, N, K,
+                             None if bias_t is None else bias_t.data_ptr(), act, acc, st)
+        assert rc == 0
+        return C.cpu().double()
+
+    tol = 1e-5 * max(1.0, ref.abs().max().item())
+    assert (run(Ad, K, 1, Bd, N, 1) - ref).abs().max() < tol                                  # NN
+    Bt = Bd.t().contiguous()
+    assert (run(Ad, K, 1, Bt, 1, K) - ref).abs().max() < tol                                  # NT
+    At = Ad.t().contiguous()
+    assert (run(At, 1, M, Bd, N, 1) - ref).abs().max() < tol                                  # TN
+    out = run(Ad, K, 1, Bt, 1, K, bias.float().to(DEV), act=1)
+    assert (out - torch.tanh(ref + bias)).abs().max() < 1e-5
+    out = run(Ad, K, 1, Bt, 1, K, bias.float().to(DEV), act=2)
+    assert (out - torch.relu(ref + bias)).abs().max() < tol
+    C0 = torch.ones(M, N, device=DEV)
+    assert (run(Ad, K, 1, Bd, N, 1, acc=1, C=C0) - (ref + 1)).abs().max() < tol
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_encode_input_matches_golden(name):
+    cfg, meta, params, batch, z = load_case(name, dtype=torch.float32)
+    model = build_model(cfg, params, train=False)
+    d = to_dev(batch)
+    enc = model.encode_input(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                             situations_input=d["situations"])
+    assert enc["encoded_situations"].shape == z["encoded_situations"].shape
+    np.testing.assert_allclose(enc["encoded_situations"].cpu().numpy(), z["encoded_situations"], atol=5e-6, rtol=1e-5)
+    np.testing.assert_allclose(enc["encoded_commands"]["encoder_outputs"].cpu().numpy(), z["encoder_outputs"],
+                               atol=5e-6, rtol=1e-5)
+    np.testing.assert_allclose(enc["hidden_states"].cpu().numpy(), z["hidden_states"], atol=5e-6, rtol=1e-5)
+    assert enc["encoded_commands"]["sequence_lengths"] == [int(l) for l in batch["cmd_lengths"]]
+    # the situation encoder is callable on its own, like the reference sub-module
+    feat = model.situation_encoder(d["situations"])
+    np.testing.assert_allclose(feat.cpu().numpy(), z["encoded_situations"], atol=5e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_forward_loss_gradients_match_golden(name):
+    cfg, meta, params, batch, z = load_case(name, dtype=torch.float32)
+    model = build_model(cfg, params, train=True)
+    d = to_dev(batch)
+    logp, aux = model(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                      situations_input=d["situations"], target_batch=d["targets"],
+                      target_lengths=batch["tgt_lengths"])
+    assert logp.shape == z["logp"].shape
+    assert np.abs(logp.detach().cpu().numpy().astype(np.float64) - z["logp"]).max() <= LOGP_ATOL
+    loss = model.get_loss(logp, d["targets"])
+    assert abs(loss.item() - float(z["nll"])) <= 1e-5 * max(1.0, abs(float(z["nll"])))
+    if cfg["auxiliary_task"]:
+        assert np.abs(aux.detach().cpu().numpy().astype(np.float64) - z["aux_logp"]).max() <= LOGP_ATOL
+        aux_loss = model.get_auxiliary_loss(aux, d["positions"])
+        assert abs(aux_loss.item() - float(z["aux_nll"])) <= 1e-5 * max(1.0, abs(float(z["aux_nll"])))
+        loss += meta["weight_target_loss"] * aux_loss       # in-place, exactly as train.py:107 does
+        assert model.get_auxiliary_accuracy(aux, d["positions"]) == pytest.approx(float(z["aux_accuracy"]))
+    else:
+        assert isinstance(aux, tuple) and len(aux) == 2      # model.py:217
+    assert abs(loss.item() - float(z["loss"])) <= 1e-5 * max(1.0, abs(float(z["loss"])))
+    acc, exact = model.get_metrics(logp, d["targets"])
+    assert acc == pytest.approx(float(z["accuracy"])) and exact == pytest.approx(float(z["exact_match"]))
+    loss.backward()
+    named = dict(model.named_parameters())
+    for pname, _ in O.param_shapes(cfg):
+        ref = torch.tensor(z["grad." + pname].astype(np.float64))
+        err = rel_l2(named[pname].grad, ref)
+        assert err <= GRAD_RTOL, f"{pname}: rel-L2 {err:.3e}"
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_greedy_decode_matches_reference_predict(name):
+    cfg, meta, params, batch, z = load_case(name, dtype=torch.float32)
+    model = build_model(cfg, params, train=False)
+    d = to_dev(batch)
+    N = int(z["greedy_max_steps"])
+    out = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], N, 1, 2, return_attention=True)
+    toks, lens, steps = out["tokens"].cpu().numpy(), out["lengths"].cpu().numpy(), out["steps"].cpu().numpy()
+    assert lens.tolist() == z["greedy_lengths"].tolist()
+    for b in range(len(lens)):
+        assert toks[b, :lens[b]].tolist() == z["greedy_sequences"][b, :lens[b]].tolist()
+        assert (toks[b, lens[b]:] == -1).all()
+        assert steps[b] == min(lens[b] + 1, N + 1)
+        tgt = batch["targets"][b, :int(batch["tgt_lengths"][b])].tolist()[1:-1]
+        assert O.sequence_accuracy(toks[b, :lens[b]].tolist(), tgt) == pytest.approx(float(z["greedy_accuracy"][b]))
+    # attention rows of kept steps are probability distributions over the valid keys
+    al = out["attention_weights_commands"].cpu().numpy()
+    be = out["attention_weights_situations"].cpu().numpy()
+    for b in range(len(lens)):
+        if lens[b]:
+            np.testing.assert_allclose(al[b, :lens[b]].sum(-1), 1.0, atol=1e-5)
+            np.testing.assert_allclose(be[b, :lens[b]].sum(-1), 1.0, atol=1e-5)
+            assert (al[b, :, int(batch["cmd_lengths"][b]):] == 0).all()
+    if cfg["auxiliary_task"]:
+        pred = out["aux_logp"].argmax(dim=1).cpu().numpy()
+        acc = 100.0 * (pred == batch["target_positions"]).astype(np.float64)
+        np.testing.assert_allclose(acc, z["greedy_aux_accuracy"])
+    # N+1 cap when EOS is unreachable (predict.py:101 uses <=)
+    out2 = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], 5, 1, -1)
+    assert out2["lengths"].cpu().tolist() == [6] * len(lens)
+    assert out2["tokens"].cpu().numpy().tolist() == z["greedy_noeos_sequences"].tolist()
+
+
+@pytest.mark.parametrize("name", ["tiny_aux", "demo", "comp_small"])
+def test_decode_input_step_api(name):
+    """predict.py's calling sequence: encode_input, key_layer x2, initialize_hidden, decode_input loop."""
+    cfg, meta, params, batch, z = load_case(name, dtype=torch.float32)
+    model = build_model(cfg, params, train=False)
+    d = to_dev(batch)
+    enc = model.encode_input(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                             situations_input=d["situations"])
+    keys_vis = model.visual_attention.key_layer(enc["encoded_situations"])
+    keys_txt = model.textual_attention.key_layer(enc["encoded_commands"]["encoder_outputs"])
+    hidden = model.attention_decoder.initialize_hidden(model.tanh(model.enc_hidden_to_dec_hidden(enc["hidden_states"])))
+    # oracle, float64
+    p64 = {k: v.double() for k, v in params.items()}
+    feat = O.cnn_forward(p64, torch.tensor(batch["situations"]).double())
+    hid, enc_out = O.encoder_forward(p64, torch.tensor(batch["commands"]), batch["cmd_lengths"])
+    kt, kv = O.project_keys(p64, enc_out, feat)
+    h, c = O.initial_state(p64, hid)
+    assert (keys_vis.cpu().double() - kv).abs().max() < 1e-5
+    assert (keys_txt.cpu().double() - kt.transpose(0, 1)).abs().max() < 1e-5
+    assert (hidden[0][0].cpu().double() - h).abs().max() < 1e-5
+    lens = torch.tensor([int(l) for l in batch["cmd_lengths"]])
+    for t in range(3):
+        tok = torch.tensor(batch["targets"][:, t])
+        logits, hidden, beta, alpha, beta2 = model.decode_input(
+            target_token=tok.to(DEV), hidden=hidden, encoder_outputs=keys_txt,
+            input_lengths=batch["cmd_lengths"], encoded_situations=keys_vis)
+        lo, h, c, al, be = O.decoder_step(p64, O.embed(p64["attention_decoder.embedding.weight"], tok), h, c, kt,
+                                          lens, kv, cfg["conditional_attention"])
+        assert hidden[0].shape == (1, len(lens), cfg["decoder_hidden_size"])
+        assert (logits.cpu().double() - lo).abs().max() < 2e-5
+        assert (hidden[0][0].cpu().double() - h).abs().max() < 1e-5
+        assert (hidden[1][0].cpu().double() - c).abs().max() < 1e-5
+        assert (alpha.cpu().double() - al).abs().max() < 1e-5
+        assert (beta.cpu().double() - be).abs().max() < 1e-5 and torch.equal(beta, beta2)
+
+
+def _random_masks(cfg, B, Ti, Tt, seed, p=0.3):
+    g = torch.Generator().manual_seed(seed)
+    M, D, E, H = cfg["grid_size"] ** 2, 3 * cfg["cnn_hidden_num_channels"], cfg["embedding_dimension"], cfg["decoder_hidden_size"]
+    mk = lambda *s: (torch.rand(*s, generator=g) > p).float() / (1 - p)
+    return {"cnn": mk(B, M, D), "enc": mk(B, Ti, E), "dec": mk(B, Tt, H)}
+
+
+@pytest.mark.parametrize("cfg_name,B,tgt", [("tiny", 5, 9), ("comp", 7, 25)])
+def test_dropout_masks_forward_backward(cfg_name, B, tgt):
+    """Train-mode arithmetic with explicit dropout masks equals the oracle with the same masks."""
+    cfg = dict(O.CONFIGS[cfg_name])
+    cfg["auxiliary_task"] = True
+    params = O.synthetic_params(cfg, 21, scale=2.0)
+    batch = O.synthetic_batch(cfg, batch_size=B, seed=22, max_cmd_len=8, min_cmd_len=3, max_tgt_len=tgt)
+    Ti, Tt = batch["commands"].shape[1], batch["targets"].shape[1]
+    masks = _random_masks(cfg, B, Ti, Tt, 5)
+    model = build_model(cfg, params, train=True)
+    d = to_dev(batch)
+    cmd_len = ops.lengths_to_device(batch["cmd_lengths"], DEV)
+    logp, aux = ops.ModelForward.apply(model._cfg(cfg["grid_size"]), d["commands"], cmd_len, Ti, d["situations"],
+                                       d["targets"], tuple(masks[k].to(DEV) for k in ("cnn", "enc", "dec")),
+                                       *model._param_list())
+    loss = model.get_loss(logp, d["targets"]) + 0.3 * model.get_auxiliary_loss(aux, d["positions"])
+    loss.backward()
+    logp_o, aux_o, loss_o, grads_o = oracle_run(cfg, params, batch, dropout=masks)
+    assert (logp.detach().cpu().double() - logp_o).abs().max() <= LOGP_ATOL
+    assert (aux.detach().cpu().double() - aux_o).abs().max() <= LOGP_ATOL
+    assert abs(loss.item() - loss_o.item()) <= 1e-5 * max(1.0, abs(loss_o.item()))
+    named = dict(model.named_parameters())
+    for pname, _ in O.param_shapes(cfg):
+        err = rel_l2(named[pname].grad, grads_o[pname])
+        assert err <= GRAD_RTOL, f"{pname}: rel-L2 {err:.3e}"
+
+
+def test_train_mode_dropout_statistics():
+    """With p > 0 and model.train() the masks are drawn internally: outputs differ between calls,
+    stay normalised, and the kept fraction matches 1-p."""
+    cfg = dict(O.CONFIGS["comp"])
+    cfg.update(encoder_dropout_p=0.3, decoder_dropout_p=0.3, cnn_dropout_p=0.1)
+    params = O.synthetic_params(cfg, 3)
+    batch = O.synthetic_batch(cfg, batch_size=16, seed=4, max_tgt_len=10)
+    model = build_model(cfg, params, train=True)
+    d = to_dev(batch)
+    args = dict(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"], situations_input=d["situations"],
+                target_batch=d["targets"], target_lengths=batch["tgt_lengths"])
+    a, _ = model(**args)
+    b, _ = model(**args)
+    assert not torch.equal(a, b)
+    assert torch.allclose(a.exp().sum(-1), torch.ones_like(a[..., 0]), atol=1e-5)
+    m = ops._dropout_mask((64, 1000), 0.3, DEV)
+    assert abs((m > 0).float().mean().item() - 0.7) < 0.01 and abs(m.max().item() - 1 / 0.7) < 1e-6
+    model.eval()
+    a, _ = model(**args)
+    b, _ = model(**args)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("cfg_name,aux,lo", [("comp", False, 3), ("comp", True, 3), ("tlen", False, 17)])
+def test_full_size_against_oracle(cfg_name, aux, lo):
+    """BASELINE.json configs 2, 3 and 5 at full size (B=200, Tt=121): forward + gradients vs the
+    float64 oracle, plus size-independent properties (normalisation, batch-split invariance)."""
+    cfg = dict(O.CONFIGS[cfg_name])
+    cfg["auxiliary_task"] = aux
+    params = O.synthetic_params(cfg, 1234)
+    batch = O.synthetic_batch(cfg, batch_size=200, seed=1235, min_tgt_len=lo)
+    assert batch["targets"].shape == (200, 121) and batch["commands"].shape == (200, 10)
+    model = build_model(cfg, params, train=True)
+    d = to_dev(batch)
+    logp, auxo = model(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                       situations_input=d["situations"], target_batch=d["targets"],
+                       target_lengths=batch["tgt_lengths"])
+    loss = model.get_loss(logp, d["targets"])
+    if aux:
+        loss = loss + 0.3 * model.get_auxiliary_loss(auxo, d["positions"])
+    loss.backward()
+    assert torch.isfinite(logp).all()
+    assert torch.allclose(logp.exp().sum(-1), torch.ones(200, 121, device=DEV), atol=1e-5)
+    logp_o, aux_o, loss_o, grads_o = oracle_run(cfg, params, batch)
+    assert (logp.detach().cpu().double() - logp_o).abs().max() <= LOGP_ATOL
+    if aux:
+        assert (auxo.detach().cpu().double() - aux_o).abs().max() <= LOGP_ATOL
+    assert abs(loss.item() - loss_o.item()) <= 1e-5 * abs(loss_o.item())
+    named = dict(model.named_parameters())
+    for pname, _ in O.param_shapes(cfg):
+        err = rel_l2(named[pname].grad, grads_o[pname])
+        assert err <= GRAD_RTOL, f"{pname}: rel-L2 {err:.3e}"
+    # batch-split invariance: examples are independent, so a ragged sub-batch reproduces its rows
+    sub = slice(37, 37 + 51)
+    sub_len = batch["cmd_lengths"][sub]
+    Ti_sub = int(sub_len.max())
+    with torch.no_grad():
+        logp_sub, _ = model(commands_input=d["commands"][sub, :Ti_sub].contiguous(), commands_lengths=sub_len,
+                            situations_input=d["situations"][sub], target_batch=d["targets"][sub],
+                            target_lengths=batch["tgt_lengths"][sub])
+    assert (logp_sub - logp[sub]).abs().max() <= 1e-5
+
+
+def test_full_size_greedy_decode_properties():
+    """Config 4: B=200, max_decoding_steps=120.  Batched result == per-example result; EOS-free run
+    emits exactly 121 tokens per sequence; prefix property in max_decoding_steps."""
+    cfg = dict(O.CONFIGS["comp"])
+    params = O.synthetic_params(cfg, 1234, scale=2.0)
+    batch = O.synthetic_batch(cfg, batch_size=200, seed=99)
+    model = build_model(cfg, params, train=False)
+    d = to_dev(batch)
+    out = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], 120, 1, 2)
+    lens = out["lengths"].cpu().numpy()
+    toks = out["tokens"].cpu().numpy()
+    assert ((lens >= 0) & (lens <= 121)).all()
+    for b in range(200):
+        assert (toks[b, :lens[b]] != 2).all() and (toks[b, :lens[b]] >= 0).all()
+    # oracle on a sample of examples
+    idx = [0, 1, 17, 63, 199]
+    seqs, *_ = O.greedy_decode(params, torch.tensor(batch["commands"][idx]), batch["cmd_lengths"][idx],
+                               torch.tensor(batch["situations"][idx]), 120)
+    for k, b in enumerate(idx):
+        assert toks[b, :lens[b]].tolist() == seqs[k]
+    # singles == batched
+    for b in (3, 150):
+        n = int(batch["cmd_lengths"][b])
+        o1 = model.greedy_decode(d["commands"][b:b + 1, :n].contiguous(), batch["cmd_lengths"][b:b + 1],
+                                 d["situations"][b:b + 1], 120, 1, 2)
+        assert o1["tokens"][0, :lens[b]].cpu().tolist() == toks[b, :lens[b]].tolist()
+        assert int(o1["lengths"][0]) == lens[b]
+    noeos = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], 120, 1, -1)
+    assert (noeos["lengths"].cpu().numpy() == 121).all() and (noeos["steps"].cpu().numpy() == 121).all()
+    short = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], 9, 1, -1)
+    assert torch.equal(short["tokens"], noeos["tokens"][:, :10])
+
+
+def test_ragged_batch_sizes_and_lengths():
+    """B not a multiple of the per-CTA tile, Tt = 1..3, Ti = 1..3, single-example batches."""
+    cfg = dict(O.CONFIGS["demo"])
+    cfg["auxiliary_task"] = True
+    params = O.synthetic_params(cfg, 5, scale=2.0)
+    for B, tmax, cmax in [(1, 3, 3), (3, 3, 4), (5, 4, 3), (9, 6, 8)]:
+        batch = O.synthetic_batch(cfg, batch_size=B, seed=B, max_cmd_len=cmax, min_cmd_len=3, max_tgt_len=tmax,
+                                  min_tgt_len=3)
+        model = build_model(cfg, params, train=True)
+        d = to_dev(batch)
+        logp, aux = model(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                          situations_input=d["situations"], target_batch=d["targets"],
+                          target_lengths=batch["tgt_lengths"])
+        loss = model.get_loss(logp, d["targets"]) + 0.3 * model.get_auxiliary_loss(aux, d["positions"])
+        loss.backward()
+        logp_o, aux_o, loss_o, grads_o = oracle_run(cfg, params, batch)
+        assert (logp.detach().cpu().double() - logp_o).abs().max() <= LOGP_ATOL
+        named = dict(model.named_parameters())
+        for pname, _ in O.param_shapes(cfg):
+            assert rel_l2(named[pname].grad, grads_o[pname]) <= GRAD_RTOL, (B, pname)
+
+
+def test_adam_step_matches_torch():
+    torch.manual_seed(0)
+    n = 100003
+    p = torch.randn(n, device=DEV)
+    g = torch.randn(n, device=DEV)
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
+        assert (p - ref.detach()).abs().max() < 1e-6
