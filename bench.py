@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the gSCAN seq2seq hot path on B200 (BASELINE.json metric: train examples/sec at
+batch 200 per GPU, plus batched greedy-decode sequences/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full training iteration of the compositional_splits shape (BASELINE.json configs[1]:
+grid 6, B=200 per GPU, k=7, E=25, H=100, Ti=10, Tt=121 - all padded steps computed as the reference
+does, paper dropout 0.3/0.3/0.1, no auxiliary task): forward + NLL loss + backward + (gradient
+all-reduce when N>1) + Adam.  Rank 0 prints ONE JSON line.
+
+  value     examples/s with the batch already resident in HBM; every step is bracketed by its own
+            CUDA events on the launching stream and L2 is flushed (256 MiB memset) between steps;
+            the per-rank totals are reduced with MAX over ranks.
+  e2e       the same step driven from pinned HOST buffers through the public API
+            (Model/FusedTrainer): H2D copies of the batch and a D2H read of the loss inside the
+            timed region, wall clock with a device synchronize at both ends.
+  roofline  the dominant kernel (decoder backward sweep) timed live with CUDA events recorded by the
+            library on the same stream (gscan_profile); the sweep is an fp32 FMA-pipe, latency-bound
+            recurrence, so its fraction of the measured bf16 tensor peak is tiny by construction -
+            the object also carries the fp32 FMA-pipe fraction and microseconds per decoder step.
+  cpu_baseline / --impl reference
+            the CPU port of the reference (oracle/gscan_oracle.py: same per-step PyTorch-eager
+            structure) on all host cores, same shape, same step definition.  /root/reference itself
+            is Python source that does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "compositional_splits: G=6 C=16 F=50 k3=7 E=25 H=100 Vi=21 V=9 B=200/GPU Ti=10 Tt=121 (all padded steps), no aux, dropout .3/.3/.1"
+SEED = 1234
+B_PER_GPU = 200
+# algorithmic FLOPs (2 per MAC) per example per decoder step inside the recurrent sweeps:
+# forward: the four dependent mat-vec stages (600+500+100+400 rows x 100) + both attentions (46 keys x 100 x 2)
+SWEEP_FWD_FLOP = 2 * (1600 * 100 + 46 * 100 * 2)
+# backward: the transposed mat-vecs (same 160k MAC) + attention backward (46 keys x 100 x 4)
+SWEEP_BWD_FLOP = 2 * (1600 * 100 + 46 * 100 * 4)
+# whole training step per example: 3 x (7.62M + 121 x 0.506M)
+STEP_FLOP_PER_EXAMPLE = 206.5e6
+
+
+def bench_cfg():
+    from multimodal_seq2seq_gscan_b200 import synthetic
+    cfg = dict(synthetic.CONFIGS["comp"])
+    cfg.update(encoder_dropout_p=0.3, decoder_dropout_p=0.3, cnn_dropout_p=0.1, auxiliary_task=False)
+    return cfg
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "sm_max_mhz": p.get("sm_max_mhz", 1965.0),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            parts = [x.strip() for x in row.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_host_batch(cfg, seed):
+    from multimodal_seq2seq_gscan_b200 import synthetic
+    return synthetic.synthetic_batch(cfg, batch_size=B_PER_GPU, seed=seed)
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port) - the only place bench.py executes oracle/
+# --------------------------------------------------------------------------------------------
+def cpu_reference_steps(cfg, steps, warmup, threads=None):
+    """forward + loss + backward + Adam on the host cores with the oracle port (train mode: dropout
+    masks drawn with torch's CPU RNG).  Returns (examples/s from the median step, list of seconds)."""
+    from oracle import gscan_oracle as O
+    threads = threads or len(os.sched_getaffinity(0))
+    torch.set_num_threads(threads)
+    params = {k: v.clone().requires_grad_(True) for k, v in O.synthetic_params(cfg, SEED).items()}
+    opt = torch.optim.Adam(list(params.values()), lr=1e-3)
+    batch = make_host_batch(cfg, SEED + 1)
+    commands, targets = torch.tensor(batch["commands"]), torch.tensor(batch["targets"])
+    situations = torch.tensor(batch["situations"])
+    B, Ti, Tt = commands.shape[0], commands.shape[1], targets.shape[1]
+    M, D, E, H = cfg["grid_size"] ** 2, 3 * cfg["cnn_hidden_num_channels"], cfg["embedding_dimension"], cfg["decoder_hidden_size"]
+
+    def mask(shape, p):
+        return None if p <= 0 else torch.empty(shape).bernoulli_(1 - p) / (1 - p)
+
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        drop = {"cnn": mask((B, M, D), cfg["cnn_dropout_p"]), "enc": mask((B, Ti, E), cfg["encoder_dropout_p"]),
+                "dec": mask((B, Tt, H), cfg["decoder_dropout_p"])}
+        logp, _ = O.model_forward(params, commands, batch["cmd_lengths"], situations, targets,
+                                  cfg["conditional_attention"], False, dropout=drop)
+        loss = O.nll_loss(logp, targets)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return B / med, times, threads
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = bench_cfg()
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 3))
+    value, times, threads = cpu_reference_steps(cfg, steps, warmup)
+    sample = f"{steps} full steps (B=200, Tt=121, fwd+loss+bwd+Adam) after {warmup} warm-up, median"
+    line = {
+        "impl": "reference", "metric": "train_examples_per_sec", "value": value, "unit": "examples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * statistics.median(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "device": "host CPU", "global_batch": B_PER_GPU},
+        "cpu_baseline": {"value": value, "unit": "examples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    import multimodal_seq2seq_gscan_b200 as pkg
+    from multimodal_seq2seq_gscan_b200 import synthetic as O
+    from multimodal_seq2seq_gscan_b200.trainer import FusedTrainer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = pkg.load()
+
+    cfg = bench_cfg()
+    model = pkg.Model(**O.model_kwargs(cfg)).to(dev)
+    model.load_state_dict(O.full_state_dict(O.synthetic_params(cfg, SEED)), strict=True)
+    trainer = FusedTrainer(model, distributed=distributed)
+    host = make_host_batch(cfg, SEED + 1 + rank)
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(host[k])).pin_memory()
+              for k in ("commands", "situations", "targets")}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    cmd_len, tgt_len = host["cmd_lengths"], host["tgt_lengths"]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def step_resident():
+        return trainer.train_step(resident["commands"], cmd_len, resident["situations"], resident["targets"], tgt_len)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+
+    # ---- value: device-resident, per-step CUDA events, L2 flush between steps -------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches0 = lib.gscan_launch_count()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        starts[i].record()
+        step_resident()
+        ends[i].record()
+    barrier()
+    launches = lib.gscan_launch_count() - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = total_ms.item() / args.steps
+    value = world * B_PER_GPU / (ms_per_step * 1e-3)
+
+    # ---- e2e: pinned host buffers -> public API -> loss read back ----------------------------------
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_times = []
+    for i in range(e2e_steps + 2):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        c = pinned["commands"].to(dev, non_blocking=True)
+        s = pinned["situations"].to(dev, non_blocking=True)
+        t = pinned["targets"].to(dev, non_blocking=True)
+        loss = trainer.train_step(c, cmd_len, s, t, tgt_len)
+        loss_host = loss.item()                      # D2H read + sync
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_times.append(dt)
+    e2e_t = torch.tensor([sum(e2e_times) / len(e2e_times)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B_PER_GPU / e2e_t.item()
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + 4 * B_PER_GPU
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline: library-recorded CUDA events around each stage, same stream ----------------------
+    lib.gscan_profile(1)
+    stage_ms = np.zeros(9)
+    n_prof = max(3, min(args.steps, 10))
+    buf = (torch.zeros(9, dtype=torch.float32)).numpy()
+    for _ in range(n_prof):
+        flush.zero_()
+        step_resident()
+        torch.cuda.synchronize()
+        lib.gscan_profile_read(buf.ctypes.data)
+        stage_ms += buf
+    lib.gscan_profile(0)
+    stage_ms /= n_prof
+    stage_names = ["encoder_side", "dec_prelude", "dec_fwd_sweep", "out_proj", "", "out_proj_bwd", "dec_bwd_sweep",
+                   "dec_wgrad_gemms", "encoder_side_bwd"]
+    stages = {n: round(float(ms), 4) for n, ms in zip(stage_names, stage_ms) if n}
+
+    # ---- greedy decode (BASELINE.json configs[3]): B=200, max_decoding_steps=120, EOS unreachable ---
+    decode = None
+    if not args.no_decode:
+        model.eval()
+        for _ in range(3):
+            model.greedy_decode(resident["commands"], cmd_len, resident["situations"], 120, 1, -1)
+        torch.cuda.synchronize()
+        n_dec = 10
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_dec)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_dec)]
+        for i in range(n_dec):
+            flush.zero_()
+            ev0[i].record()
+            out = model.greedy_decode(resident["commands"], cmd_len, resident["situations"], 120, 1, -1)
+            ev1[i].record()
+        torch.cuda.synchronize()
+        dec_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1)) / n_dec
+        decode = {"seqs_per_sec": B_PER_GPU / (dec_ms * 1e-3), "steps_per_sec": B_PER_GPU * 121 / (dec_ms * 1e-3),
+                  "ms_per_batch": dec_ms, "batch": B_PER_GPU, "steps_per_seq": 121, "n_gpus": 1,
+                  "note": "EOS unreachable: every sequence runs all 121 steps (worst case)"}
+        model.train()
+
+    if rank == 0:
+        peaks = read_peaks()
+        Tt = host["targets"].shape[1]
+        bwd_ms = stages["dec_bwd_sweep"]
+        achieved_tflops = B_PER_GPU * Tt * SWEEP_BWD_FLOP / (bwd_ms * 1e-3) / 1e12
+        sm_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        roofline = {
+            "kernel": "decoder_bwd_kernel (BPTT sweep over all 121 steps)", "bound": "tensor",
+            "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+            "frac": achieved_tflops / peaks["bf16_tflops"], "peak_source": peaks["source"], "traffic": None,
+            "note": "fp32 FMA-pipe recurrence (1e-4 parity rules out bf16 operands): latency/issue bound, "
+                    "not tensor or HBM bound; see frac_fp32_fma and us_per_decoder_step",
+            "fp32_fma_peak_tflops": fp32_peak, "frac_fp32_fma": achieved_tflops / fp32_peak,
+            "kernel_ms": bwd_ms, "us_per_decoder_step": 1e3 * bwd_ms / Tt,
+            "fwd_sweep_ms": stages["dec_fwd_sweep"], "fwd_us_per_decoder_step": 1e3 * stages["dec_fwd_sweep"] / Tt,
+            "fwd_frac_fp32_fma": B_PER_GPU * Tt * SWEEP_FWD_FLOP / (stages["dec_fwd_sweep"] * 1e-3) / 1e12 / fp32_peak,
+            "stage_ms": stages,
+            "whole_step_tflops": value * STEP_FLOP_PER_EXAMPLE / 1e12,
+        }
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, times, threads = cpu_reference_steps(cfg, steps=7, warmup=2)
+            cpu_baseline = {"value": v, "unit": "examples/s", "cores": threads, "kind": "port",
+                            "sample": "7 full steps (B=200, Tt=121, fwd+loss+bwd+Adam) after 2 warm-up; median "
+                                      f"{statistics.median(times):.3f} s, min {min(times):.3f} s"}
+        line = {
+            "metric": "train_examples_per_sec", "value": value, "unit": "examples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU,
+                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "step": "forward + NLL + backward + " + ("gradient all-reduce (NCCL) + " if world > 1 else "")
+                               + "fused Adam",
+                       "l2": "flushed between timed steps (256 MiB memset); the step's own workspace (~300 MB) "
+                             "also exceeds L2"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "examples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": 1e3 * e2e_t.item(), "last_loss": loss_host},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "decode": decode,
+        }
+        print(json.dumps(line))
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

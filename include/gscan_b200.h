@@ -73,6 +73,24 @@ typedef struct gscan_dims {
 
 int gscan_abi_version(void);
 
+/* Number of kernels this library has launched in this process (memsets / copies not counted). */
+unsigned long long gscan_launch_count(void);
+
+/*
+ * Stage timing for bench.py / profiling.  After gscan_profile(1), gscan_forward and gscan_backward
+ * record CUDA events on the caller's stream at their stage boundaries; gscan_profile_read waits for
+ * them and writes GSCAN_NUM_STAGES durations in milliseconds (-1 for a stage that did not run):
+ *   0 CNN + command encoder + key projections     1 weight packing + target embeddings + gate pre-GEMM
+ *   2 decoder forward sweep (all Tt steps)        3 output projection + log-softmax (+ aux head)
+ *   4 (unused seam between forward and backward)  5 output-projection backward
+ *   6 decoder backward sweep (BPTT)               7 decoder weight-gradient GEMMs + embedding scatter
+ *   8 CNN / key / initial-state / encoder backward
+ * Not thread safe; intended for single-stream measurement.
+ */
+#define GSCAN_NUM_STAGES 9
+int gscan_profile(int enable);
+int gscan_profile_read(float* stage_ms /* [GSCAN_NUM_STAGES] */);
+
 /* 0 if the kernels support this shape, GSCAN_E_UNSUPPORTED otherwise. */
 int gscan_check_dims(const gscan_dims* d);
 

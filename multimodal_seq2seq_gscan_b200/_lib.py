@@ -35,6 +35,9 @@ ParamArray = c_void_p * NUM_PARAMS
 # name -> (restype, argtypes); exactly the symbols include/gscan_b200.h declares
 SIGNATURES = {
     "gscan_abi_version": (c_int32, []),
+    "gscan_launch_count": (ctypes.c_ulonglong, []),
+    "gscan_profile": (c_int32, [c_int32]),
+    "gscan_profile_read": (c_int32, [c_void_p]),
     "gscan_check_dims": (c_int32, [POINTER(Dims)]),
     "gscan_workspace_floats": (c_size_t, [POINTER(Dims)]),
     "gscan_encode_workspace_floats": (c_size_t, [POINTER(Dims)]),

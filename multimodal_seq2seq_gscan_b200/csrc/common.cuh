@@ -4,8 +4,12 @@
 #include <stdint.h>
 #include <math.h>
 
+// every kernel launch of the library goes through this macro, which also counts launches
+// (gscan_launch_count) so that callers can state how many of OUR kernels ran in a timed region
+namespace gscan { inline unsigned long long& launch_counter() { static unsigned long long c = 0; return c; } }
 #define GSCAN_CHECK_LAUNCH()                         \
   do {                                               \
+    ++gscan::launch_counter();                       \
     cudaError_t e__ = cudaGetLastError();            \
     if (e__ != cudaSuccess) return (int)e__;         \
   } while (0)

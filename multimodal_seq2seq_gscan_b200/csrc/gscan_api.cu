@@ -38,6 +38,23 @@ int num_sms() {
   return n;
 }
 
+// ---- optional stage profiling (CUDA events recorded on the caller's stream) ------------------
+constexpr int kNumStages = GSCAN_NUM_STAGES;
+bool g_profile = false;
+cudaEvent_t g_events[kNumStages + 1];
+bool g_events_created = false;
+bool g_stage_seen[kNumStages + 1];
+
+void prof_mark(int idx, cudaStream_t st) {
+  if (!g_profile) return;
+  if (!g_events_created) {
+    for (auto& e : g_events) cudaEventCreate(&e);
+    g_events_created = true;
+  }
+  cudaEventRecord(g_events[idx], st);
+  g_stage_seen[idx] = true;
+}
+
 // ---- workspace layout --------------------------------------------------------------------
 struct Layout {
   size_t total = 0;
@@ -339,6 +356,28 @@ extern "C" {
 
 int gscan_abi_version(void) { return GSCAN_ABI_VERSION; }
 
+unsigned long long gscan_launch_count(void) { return launch_counter(); }
+
+int gscan_profile(int enable) {
+  g_profile = enable != 0;
+  for (auto& s : g_stage_seen) s = false;
+  return GSCAN_OK;
+}
+
+int gscan_profile_read(float* stage_ms) {
+  if (!stage_ms) return GSCAN_E_BADARG;
+  // stage i spans events i -> i+1, except the forward/backward seam (4 -> 5)
+  for (int i = 0; i < kNumStages; ++i) {
+    stage_ms[i] = -1.f;
+    if (i == 4 || !g_stage_seen[i] || !g_stage_seen[i + 1]) continue;
+    TRYCUDA(cudaEventSynchronize(g_events[i + 1]));
+    float ms = 0.f;
+    TRYCUDA(cudaEventElapsedTime(&ms, g_events[i], g_events[i + 1]));
+    stage_ms[i] = ms;
+  }
+  return GSCAN_OK;
+}
+
 int gscan_check_dims(const gscan_dims* d) {
   if (!d) return GSCAN_E_BADARG;
   if (d->B < 1 || d->Ti < 1 || d->Tt < 1 || d->G < 1 || d->C < 1 || d->F < 1 || d->K3 < 1 || d->E < 1 || d->H < 4 ||
@@ -390,7 +429,9 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   const long long* cmds = reinterpret_cast<const long long*>(commands);
   const long long* tgts = reinterpret_cast<const long long*>(targets);
 
+  prof_mark(0, st);
   TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, st));
+  prof_mark(1, st);
   TRY(pack_decoder_weights(*d, P, ws, L, st));
   // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
   {
@@ -411,7 +452,9 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   p.Xe = ws + L.Xe;
   p.U = ws + L.U; p.Cs = ws + L.Cs; p.gates = ws + L.gates; p.alpha = ws + L.alpha; p.beta = ws + L.beta;
   p.Qp = ws + L.Qp; p.qT = ws + L.qT; p.qV = ws + L.qV; p.beta_sum = ws + L.beta_sum;
+  prof_mark(2, st);
   TRY(launch_dec_fwd(*d, p, false, st));
+  prof_mark(3, st);
   // output projection for all steps at once, then log-softmax
   TRY(linear(U1, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre, H, Tt * B, H, 4 * H, nullptr, nullptr, 0, st));
   {
@@ -427,6 +470,7 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
     GSCAN_CHECK_LAUNCH();
     TRYCUDA(cudaMemcpyAsync(aux_logp, ws + L.aux_logp, sizeof(float) * (size_t)B * M, cudaMemcpyDeviceToDevice, st));
   }
+  prof_mark(4, st);
   return GSCAN_OK;
 }
 
@@ -452,6 +496,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   float* U1 = ws + L.U + (size_t)B * 4 * H;
 
   // B1: log-softmax backward, hidden_to_output
+  prof_mark(5, st);
   {
     int blocks = min(ceil_div(R, 8), 8 * sms);
     logsoftmax_bwd_kernel<<<blocks, 256, 0, st>>>(d_logp, ws + L.logp, V, B, Tt, ws + L.dlogits);
@@ -483,7 +528,9 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   bp.dgates = ws + L.dgates; bp.dd = ws + L.dd; bp.dqV = ws + L.dqV; bp.dqT = ws + L.dqT;
   bp.dKT = ws + L.dKT; bp.dKV = ws + L.dKV; bp.dh0 = ws + L.dh0;
   bp.dvT = ws + L.dvec; bp.dvV = ws + L.dvec + H;
+  prof_mark(6, st);
   TRY(launch_dec_bwd(*d, bp, st));
+  prof_mark(7, st);
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   // B5: decoder weight gradients as batched "TN" products over all steps
@@ -511,6 +558,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     GSCAN_CHECK_LAUNCH();
   }
   // B6: visual keys -> CNN
+  prof_mark(8, st);
   TRY(launch_grad_gemm(ws + L.dKV, H, ws + L.feat, D, G[GSCAN_P_VIS_KEY_W], D, H, D, B * M, sms, st));
   TRY(matmul_nn(ws + L.dKV, H, P[GSCAN_P_VIS_KEY_W], D, ws + L.dfeat, D, B * M, D, H, 0, st));
   {
@@ -571,6 +619,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
         use_smem);
     GSCAN_CHECK_LAUNCH();
   }
+  prof_mark(9, st);
   return GSCAN_OK;
 }
 

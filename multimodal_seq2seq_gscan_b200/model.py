@@ -242,10 +242,11 @@ class Model(nn.Module):
 
     def get_loss(self, target_scores: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """Mean NLL of [B,Tt,V] log-probabilities against targets shifted left by one, ignoring pad."""
-        return ops.NLLLoss.apply(target_scores, targets, self.target_pad_idx, 1)
+        return ops.NLLLoss.apply(target_scores, targets, self.target_pad_idx, 1)[0]
 
     def get_auxiliary_loss(self, auxiliary_scores_target: torch.Tensor, target_target_positions: torch.Tensor):
-        return ops.NLLLoss.apply(auxiliary_scores_target.unsqueeze(1), target_target_positions.view(-1, 1), -100, 0)
+        return ops.NLLLoss.apply(auxiliary_scores_target.unsqueeze(1), target_target_positions.view(-1, 1),
+                                 -100, 0)[0]
 
     def auxiliary_task_forward(self, output_scores_target_pos: torch.Tensor) -> torch.Tensor:
         assert self.auxiliary_task, "Please set auxiliary_task to True if using it."

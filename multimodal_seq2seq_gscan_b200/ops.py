@@ -134,9 +134,8 @@ class ModelForward(torch.autograd.Function):
             d_aux = d_aux.contiguous().float()
         # one flat fp32 gradient buffer in model.parameters() order; the per-parameter gradients
         # returned to autograd are views into it (this is also the data-parallel all-reduce buffer)
-        sizes = [0 if s is None else int(np.prod(s)) for s in ctx.param_shapes]
-        offsets = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])])
-        flat = torch.empty(int(offsets[-1]), dtype=torch.float32, device=dev)
+        sizes, offsets = flat_layout(ctx.param_shapes)
+        flat = torch.zeros(int(offsets[-1]), dtype=torch.float32, device=dev)
         views = [None if s is None else flat[int(o):int(o) + n].view(s)
                  for s, o, n in zip(ctx.param_shapes, offsets[:-1], sizes)]
         rc = lib.gscan_backward(dims, _param_array(params), _ptr(commands), _ptr(cmd_len_dev), _ptr(situations),
@@ -147,8 +146,19 @@ class ModelForward(torch.autograd.Function):
         return (None, None, None, None, None, None, None, *views)
 
 
+def flat_layout(shapes):
+    """Offsets (in floats, each padded to a multiple of 4 = 16 bytes) of the tensors of a flat fp32
+    buffer in model.parameters() order; absent tensors (shape None) take no room.  Used for the flat
+    gradient buffer produced by ``ModelForward.backward`` and for ``FusedTrainer``'s flat parameter /
+    Adam-state buffers, so the two line up element for element."""
+    sizes = [0 if s is None else int(np.prod(s)) for s in shapes]
+    offsets = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])]).astype(np.int64)
+    return sizes, offsets
+
+
 class NLLLoss(torch.autograd.Function):
-    """Mean NLL over non-ignored targets shifted by ``shift`` (gscan_nll_forward / _backward)."""
+    """(mean NLL over non-ignored targets shifted by ``shift``, number of scored targets)
+    (gscan_nll_forward / _backward)."""
 
     @staticmethod
     def forward(ctx, logp, targets, pad_idx, shift):
@@ -163,10 +173,12 @@ class NLLLoss(torch.autograd.Function):
         _call_counts["other"] += 1
         ctx.save_for_backward(targets, out)
         ctx.meta = (B, T, V, int(pad_idx), int(shift))
-        return out[0].clone()
+        count = out[1].clone()
+        ctx.mark_non_differentiable(count)
+        return out[0].clone(), count
 
     @staticmethod
-    def backward(ctx, d_loss):
+    def backward(ctx, d_loss, _d_count):
         lib = _lib.load()
         targets, out = ctx.saved_tensors
         B, T, V, pad_idx, shift = ctx.meta
