@@ -2,14 +2,17 @@
 // sequences for forward / backward / encode / decode-step / greedy decode.
 #include "../../include/gscan_b200.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "cnn.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "misc.cuh"
 #include "recurrent.cuh"
+#include "decoder_cluster.cuh"
 
 using namespace gscan;
 
@@ -66,6 +69,7 @@ struct Layout {
   // forward (saved)
   size_t Wt_cnn, feat, KV, enc_x, xg[2], enc_h[2], enc_c[2], enc_g[2], enc_out, h_enc, KT, h0;
   size_t WA_t, WB_t, WC_t, WD_t, WhhE_t[2];
+  size_t WA2, WC2, WD2, PT;   // cluster-resident decoder sweep (decoder_cluster.cuh)
   size_t U, Xe, Cs, gates, alpha, beta, Qp, qT, qV, beta_sum, aux_logp, pre, logp;
   // backward scratch
   size_t dlogits, dpre, dU, dgates, dd, dqV, dqT, dKT, dKV, dh0, dbeta_aux, dfeat, dconv, dWt_cnn;
@@ -96,6 +100,10 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
   L.WC_t = L.take(H * H);
   L.WD_t = L.take(H * 4 * H);
   for (int i = 0; i < 2; ++i) L.WhhE_t[i] = L.take(H * 4 * H);
+  L.WA2 = L.take(H * L.RA);
+  L.WC2 = L.take(H * H);
+  L.WD2 = L.take(H * 4 * H);
+  L.PT = L.take(Ti * B * (size_t)L.RB);
   L.U = L.take((Tt + 1) * B * 4 * H);
   L.Xe = L.take(Tt * B * 4 * H);
   L.Cs = L.take((Tt + 1) * B * H);
@@ -212,6 +220,7 @@ int launch_dec_bwd(const gscan_dims& d, const DecBwdP& p, cudaStream_t st) {
   if (nb == 2) return launch_dec_bwd_t<2>(p, dec_smem_bytes<2>(d, 0, 0, true, false), st);
   return launch_dec_bwd_t<1>(p, dec_smem_bytes<1>(d, 0, 0, true, false), st);
 }
+
 
 int enc_nb(const gscan_dims& d) {
   int nb = 2;
@@ -349,6 +358,148 @@ void fill_dec_fwd_common(const gscan_dims& d, const float* const* P, float* ws, 
   p.bc = P[GSCAN_P_COND_B];
 }
 
+// ---- cluster-resident decoder sweep (v2) ----------------------------------------------------------
+struct ClusterCfg { int C = 0, NB = 0; ClFwdSmem smem; };
+
+int env_dec_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* s = getenv("GSCAN_DEC_VERSION");
+    v = s ? atoi(s) : 2;
+  }
+  return v;
+}
+
+template <int NB>
+cudaError_t cl_fwd_launch(const DecFwd2P& p, const ClFwdSmem& sm, int nclusters, cudaStream_t st, int* max_clusters) {
+  auto kern = decoder_fwd_cluster_kernel<NB>;
+  size_t bytes = sm.total * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(nclusters * p.C);
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = p.C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters) return cudaOccupancyMaxActiveClusters(max_clusters, kern, &cfg);
+  return cudaLaunchKernelEx(&cfg, kern, p, sm);
+}
+
+cudaError_t cl_fwd_dispatch(int NB, const DecFwd2P& p, const ClFwdSmem& sm, int nclusters, cudaStream_t st,
+                            int* max_clusters) {
+  switch (NB) {
+    case 1: return cl_fwd_launch<1>(p, sm, nclusters, st, max_clusters);
+    case 2: return cl_fwd_launch<2>(p, sm, nclusters, st, max_clusters);
+    case 3: return cl_fwd_launch<3>(p, sm, nclusters, st, max_clusters);
+    case 4: return cl_fwd_launch<4>(p, sm, nclusters, st, max_clusters);
+    case 5: return cl_fwd_launch<5>(p, sm, nclusters, st, max_clusters);
+    case 6: return cl_fwd_launch<6>(p, sm, nclusters, st, max_clusters);
+    case 7: return cl_fwd_launch<7>(p, sm, nclusters, st, max_clusters);
+    case 8: return cl_fwd_launch<8>(p, sm, nclusters, st, max_clusters);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// Cluster size and examples per cluster for this shape; C == 0 means "use the v1 kernels".
+// Cost model: per-step time ~ (slice width) x (examples per cluster); clusters must all be co-resident.
+ClusterCfg pick_cluster_cfg(const gscan_dims& d) {
+  thread_local gscan_dims cached_d{};
+  thread_local ClusterCfg cached{};
+  thread_local bool have = false;
+  if (have && memcmp(&cached_d, &d, sizeof(d)) == 0) return cached;
+  ClusterCfg best{};
+  if (env_dec_version() >= 2) {
+    const int M = d.G * d.G;
+    long best_cost = -1;
+    for (int C = 8; C >= 2; --C) {
+      if (d.H % (4 * C) != 0) continue;
+      const int hs = d.H / C;
+      if (hs * (5 + d.conditional_attention) > 32 * kClWarps) continue;
+      int NB = min(kClMaxNB, max(1, ceil_div(d.B, max(1, num_sms() / C))));
+      for (; NB <= kClMaxNB; ++NB) {
+        if (NB * 4 * hs > 2 * kClThreads || NB > kClWarps) break;
+        ClFwdSmem sm = cl_fwd_smem(NB, C, d.H, d.Ti, M, d.conditional_attention);
+        if (sm.total * sizeof(float) > kMaxSmemBytes) break;
+        DecFwd2P p{};
+        p.C = C;
+        int max_clusters = 0;
+        if (cl_fwd_dispatch(NB, p, sm, ceil_div(d.B, NB), nullptr, &max_clusters) != cudaSuccess) {
+          cudaGetLastError();
+          break;
+        }
+        const int ncl = ceil_div(d.B, NB);
+        if (max_clusters < 1) break;
+        const int waves = ceil_div(ncl, max_clusters);
+        if (waves > 1 && NB < kClMaxNB) continue;   // try more examples per cluster first
+        long cost = (long)hs * NB * waves;
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost;
+          best.C = C;
+          best.NB = NB;
+          best.smem = sm;
+        }
+        break;
+      }
+    }
+  }
+  if (getenv("GSCAN_DEBUG"))
+    fprintf(stderr, "[gscan] decoder sweep config: B=%d H=%d -> C=%d NB=%d clusters=%d smem=%zu B\n", d.B, d.H, best.C, best.NB,
+            best.NB ? ceil_div(d.B, best.NB) : 0, best.smem.total * sizeof(float));
+  cached_d = d;
+  cached = best;
+  have = true;
+  return best;
+}
+
+int launch_dec_fwd_cluster(const gscan_dims& d, const float* const* P, float* ws, const Layout& L, const ClusterCfg& cc,
+                           DecFwd2P p, cudaStream_t st) {
+  const int H = d.H, hs = H / cc.C;
+  ClusterPackP pk{P[GSCAN_P_TXT_QUERY_W], P[GSCAN_P_COND_W], P[GSCAN_P_DEC_WHH], P[GSCAN_P_VIS_QUERY_W],
+                  P[GSCAN_P_DEC_WIH], ws + L.WA2, ws + L.WC2, ws + L.WD2, H, cc.C, hs, d.conditional_attention};
+  pack_cluster_kernel<<<min(2 * num_sms(), ceil_div(H * (L.RA + 5 * H), 256)), 256, 0, st>>>(pk);
+  GSCAN_CHECK_LAUNCH();
+  // P = K^T . [W_c[:, H:2H] ; W_ih[:, H:2H]]^T for every command position
+  float* PT = ws + L.PT;
+  const int cH = d.conditional_attention ? H : 0;
+  if (cH) TRY(linear(p.KT, H, P[GSCAN_P_COND_W] + H, 2 * H, PT, L.RB, d.Ti * d.B, H, H, nullptr, nullptr, 0, st));
+  TRY(linear(p.KT, H, P[GSCAN_P_DEC_WIH] + H, 3 * H, PT + cH, L.RB, d.Ti * d.B, 4 * H, H, nullptr, nullptr, 0, st));
+  p.C = cc.C; p.hs = hs;
+  p.WA = ws + L.WA2; p.WC = ws + L.WC2; p.WD = ws + L.WD2; p.PT = PT;
+  static const bool want_timeline = getenv("GSCAN_TIMELINE") != nullptr;   // debug only: allocates and synchronises
+  long long* tl = nullptr;
+  if (want_timeline) {
+    cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
+    p.timeline = tl;
+  }
+  TRYCUDA(cl_fwd_dispatch(cc.NB, p, cc.smem, ceil_div(d.B, cc.NB), st, nullptr));
+  ++launch_counter();
+  if (tl) {
+    std::vector<long long> h(16 * (size_t)p.T);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), tl, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+    cudaFree(tl);
+    double acc[16] = {0};
+    int n = 0;
+    for (int t = 2; t + 1 < p.T; ++t, ++n) {
+      for (int k = 0; k < 15; ++k) acc[k] += (double)(h[t * 16 + k + 1] - h[t * 16 + k]);
+      acc[15] += (double)(h[(t + 1) * 16] - h[t * 16 + 15]);
+    }
+    fprintf(stderr, "[gscan] fwd cluster timeline (avg cycles per phase over %d steps):", n);
+    double tot = 0;
+    for (int k = 0; k < 16; ++k) { fprintf(stderr, " %d:%.0f", k, acc[k] / n); tot += acc[k] / n; }
+    fprintf(stderr, " total %.0f\n", tot);
+  }
+  return 0;
+}
+
+
 }  // namespace
 
 // =================================================================================================
@@ -453,7 +604,18 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   p.U = ws + L.U; p.Cs = ws + L.Cs; p.gates = ws + L.gates; p.alpha = ws + L.alpha; p.beta = ws + L.beta;
   p.Qp = ws + L.Qp; p.qT = ws + L.qT; p.qV = ws + L.qV; p.beta_sum = ws + L.beta_sum;
   prof_mark(2, st);
-  TRY(launch_dec_fwd(*d, p, false, st));
+  const ClusterCfg cc = pick_cluster_cfg(*d);
+  if (cc.C) {
+    DecFwd2P p2{};
+    p2.B = B; p2.T = Tt; p2.Ti = d->Ti; p2.M = M; p2.H = H; p2.cond = d->conditional_attention;
+    p2.vT = p.vT; p2.vV = p.vV; p2.bc = p.bc;
+    p2.KT = p.KT; p2.KV = p.KV; p2.cmd_len = cmd_len; p2.h_init = p.h_init; p2.c_init = p.c_init; p2.Xe = p.Xe;
+    p2.U = p.U; p2.Cs = p.Cs; p2.gates = p.gates; p2.alpha = p.alpha; p2.beta = p.beta;
+    p2.Qp = p.Qp; p2.qT = p.qT; p2.qV = p.qV; p2.beta_sum = p.beta_sum;
+    TRY(launch_dec_fwd_cluster(*d, P, ws, L, cc, p2, st));
+  } else {
+    TRY(launch_dec_fwd(*d, p, false, st));
+  }
   prof_mark(3, st);
   // output projection for all steps at once, then log-softmax
   TRY(linear(U1, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre, H, Tt * B, H, 4 * H, nullptr, nullptr, 0, st));
