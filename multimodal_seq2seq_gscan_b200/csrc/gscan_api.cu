@@ -13,6 +13,7 @@
 #include "misc.cuh"
 #include "recurrent.cuh"
 #include "decoder_cluster.cuh"
+#include "decoder_v3.cuh"
 
 using namespace gscan;
 
@@ -365,7 +366,7 @@ int env_dec_version() {
   static int v = -1;
   if (v < 0) {
     const char* s = getenv("GSCAN_DEC_VERSION");
-    v = s ? atoi(s) : 2;
+    v = s ? atoi(s) : 3;
   }
   return v;
 }
@@ -500,6 +501,97 @@ int launch_dec_fwd_cluster(const gscan_dims& d, const float* const* P, float* ws
 }
 
 
+// ---- register-resident cluster sweep (v3, decoder_v3.cuh): H = 100, 6x6 grid only ---------------------
+template <bool COND>
+int v3_fwd_prepare(size_t bytes) {
+  static bool done = false, ok = false;
+  static size_t done_bytes = 0;
+  if (done && bytes <= done_bytes) return ok ? 0 : GSCAN_E_UNSUPPORTED;
+  auto kern = v3::dec_fwd_v3_kernel<COND>;
+  ok = false;
+  done = true;
+  done_bytes = bytes;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return GSCAN_E_UNSUPPORTED;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(v3::kC);
+  cfg.blockDim = dim3(v3::kThreads);
+  cfg.dynamicSmemBytes = bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = v3::kC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    return GSCAN_E_UNSUPPORTED;
+  }
+  if (getenv("GSCAN_DEBUG")) fprintf(stderr, "[gscan] v3 fwd sweep: smem %zu B, max co-resident clusters %d\n", bytes, max_clusters);
+  ok = true;
+  return 0;
+}
+
+bool v3_shape_ok(const gscan_dims& d) {
+  return env_dec_version() >= 3 && d.H == v3::kH && d.G * d.G == v3::kM && d.Ti <= v3::kMaxTi;
+}
+
+// P = K^T . [W_c[:, H:2H] ; W_ih[:, H:2H]]^T for every command position
+int compute_PT(const gscan_dims& d, const float* const* P, const float* KT, float* PT, int RB, cudaStream_t st) {
+  const int H = d.H;
+  const int cH = d.conditional_attention ? H : 0;
+  if (cH) TRY(linear(KT, H, P[GSCAN_P_COND_W] + H, 2 * H, PT, RB, d.Ti * d.B, H, H, nullptr, nullptr, 0, st));
+  TRY(linear(KT, H, P[GSCAN_P_DEC_WIH] + H, 3 * H, PT + cH, RB, d.Ti * d.B, 4 * H, H, nullptr, nullptr, 0, st));
+  return 0;
+}
+
+void print_timeline(const char* what, long long* tl, int T, cudaStream_t st) {
+  std::vector<long long> h(16 * (size_t)T);
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h.data(), tl, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
+  cudaFree(tl);
+  double acc[16] = {0};
+  int n = 0;
+  for (int t = 2; t + 1 < T; ++t, ++n) {
+    for (int k = 0; k < 15; ++k) acc[k] += (double)(h[t * 16 + k + 1] - h[t * 16 + k]);
+    acc[15] += (double)(h[(t + 1) * 16] - h[t * 16 + 15]);
+  }
+  if (n == 0) return;
+  fprintf(stderr, "[gscan] %s timeline (avg cycles per phase over %d steps):", what, n);
+  double tot = 0;
+  for (int k = 0; k < 16; ++k) { fprintf(stderr, " %d:%.0f", k, acc[k] / n); tot += acc[k] / n; }
+  fprintf(stderr, " total %.0f\n", tot);
+}
+
+int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, const Layout& L, v3::DecFwd3P p,
+                      cudaStream_t st) {
+  const int cond = d.conditional_attention ? 1 : 0;
+  const v3::FwdSmem sm = v3::fwd_smem(d.Ti, cond);
+  const size_t bytes = (size_t)sm.total * sizeof(float);
+  if (bytes > kMaxSmemBytes) return GSCAN_E_UNSUPPORTED;
+  TRY(cond ? v3_fwd_prepare<true>(bytes) : v3_fwd_prepare<false>(bytes));
+  TRY(compute_PT(d, P, p.KT, ws + L.PT, L.RB, st));
+  p.PT = ws + L.PT;
+  p.W_qT = P[GSCAN_P_TXT_QUERY_W]; p.W_c = P[GSCAN_P_COND_W]; p.W_hh = P[GSCAN_P_DEC_WHH];
+  p.W_qV = P[GSCAN_P_VIS_QUERY_W]; p.W_ih = P[GSCAN_P_DEC_WIH];
+  static const bool want_timeline = getenv("GSCAN_TIMELINE") != nullptr;   // debug only: allocates and synchronises
+  long long* tl = nullptr;
+  if (want_timeline) {
+    cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
+    p.timeline = tl;
+  }
+  const int grid = ceil_div(d.B, v3::kNB) * v3::kC;
+  if (cond) v3::dec_fwd_v3_kernel<true><<<grid, v3::kThreads, bytes, st>>>(p);
+  else v3::dec_fwd_v3_kernel<false><<<grid, v3::kThreads, bytes, st>>>(p);
+  GSCAN_CHECK_LAUNCH();
+  if (tl) print_timeline("v3 fwd", tl, p.T, st);
+  return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -604,8 +696,21 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   p.U = ws + L.U; p.Cs = ws + L.Cs; p.gates = ws + L.gates; p.alpha = ws + L.alpha; p.beta = ws + L.beta;
   p.Qp = ws + L.Qp; p.qT = ws + L.qT; p.qV = ws + L.qV; p.beta_sum = ws + L.beta_sum;
   prof_mark(2, st);
-  const ClusterCfg cc = pick_cluster_cfg(*d);
-  if (cc.C) {
+  const ClusterCfg cc = v3_shape_ok(*d) ? ClusterCfg{} : pick_cluster_cfg(*d);
+  bool v3_done = false;
+  if (v3_shape_ok(*d)) {
+    v3::DecFwd3P p3{};
+    p3.B = B; p3.T = Tt; p3.Ti = d->Ti;
+    p3.vT = p.vT; p3.vV = p.vV; p3.bc = p.bc;
+    p3.KT = p.KT; p3.KV = p.KV; p3.cmd_len = cmd_len; p3.h_init = p.h_init; p3.c_init = p.c_init; p3.Xe = p.Xe;
+    p3.U = p.U; p3.Cs = p.Cs; p3.gates = p.gates; p3.alpha = p.alpha; p3.beta = p.beta;
+    p3.Qp = p.Qp; p3.qT = p.qT; p3.qV = p.qV; p3.beta_sum = p.beta_sum;
+    int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, st);
+    if (rc == 0) v3_done = true;
+    else if (rc != GSCAN_E_UNSUPPORTED) return rc;
+  }
+  if (v3_done) {
+  } else if (cc.C) {
     DecFwd2P p2{};
     p2.B = B; p2.T = Tt; p2.Ti = d->Ti; p2.M = M; p2.H = H; p2.cond = d->conditional_attention;
     p2.vT = p.vT; p2.vV = p.vV; p2.bc = p.bc;
