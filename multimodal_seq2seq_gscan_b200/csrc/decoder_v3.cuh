@@ -3,9 +3,12 @@
 // H = 100, 6x6 grid: a cluster of 5 CTAs owns 8 examples for the whole sequence, CTA r owns the
 // hidden slice [20r, 20r+20) of every H-sized quantity.
 //
-//  * Recurrent weights live in REGISTERS for the whole sweep: every thread owns a fixed
-//    (row pair, k-slice) tile of each mat-vec stage, so the time loop reads no weights at all
-//    (v1 streamed ~640 KB/step/CTA from L2, v2 re-read 88 KB/step/CTA from shared memory).
+//  * Recurrent weights are resident for the whole sweep as tensor-core operand fragments: every
+//    mat-vec stage is a [16 rows x K] x [K x 8 examples] product on mma.sync.m16n8k8 (tf32) in
+//    split precision (3xTF32: W_hi x_hi + W_lo x_hi + W_hi x_lo, fp32 accumulate, ~2^-21 relative
+//    error), the W_hi fragments live in registers, the W_lo fragments in shared memory
+//    (v1 streamed ~640 KB/step/CTA from L2, v2 re-read 88 KB/step/CTA from shared memory; the
+//    fp32 FFMA2 tile kept below for tools/ubench_mv2.cu is operand-bandwidth bound at ~50 FMA/clk/SM).
 //  * CTAs exchange activations with one-sided stores into each other's shared memory
 //    (st.async ... mbarrier::complete_tx): the receiver waits on a local mbarrier whose
 //    transaction count covers the bytes of all 5 senders.  There is no cluster-wide barrier in
@@ -18,8 +21,9 @@
 namespace gscan {
 namespace v3 {
 
-constexpr int kH = 100, kC = 5, kHS = 20, kM = 36, kG4 = 80, kNB = 8, kThreads = 256;
-constexpr int kXS = 100;   // row stride of the gathered activation vectors
+constexpr int kH = 100, kC = 5, kHS = 20, kM = 36, kG4 = 80, kNB = 8, kThreads = 512;
+constexpr int kXS = 104;   // row stride of the gathered activation vectors (13 k-steps of 8; pad stays zero)
+constexpr int kKSteps = 13;
 constexpr int kGS = 84;    // row stride of the gate pre-activation scratch (bank spread)
 constexpr int kMaxTi = 16;
 
@@ -77,9 +81,41 @@ __device__ __forceinline__ float4 lds4(const float* p) { return *reinterpret_cas
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
+// ---- split-precision tensor-core mat-vec ----------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xffffe000u; }
+__device__ __forceinline__ uint32_t tf32_lo(float x) { return __float_as_uint(x - __uint_as_float(tf32_hi(x))); }
+
+// One 16-row tile: o = W[16 x 104] . x[8 examples][104]^T.  Lane (g = lane>>2, t = lane&3) supplies
+// for k-step s the operand slots (k = t, t+4) from the physical columns (8s + 2t, 8s + 2t + 1), for A
+// and B alike, so both come from 8-byte loads.  Result: o[0], o[1] = row g, examples 2t, 2t+1;
+// o[2], o[3] = row g + 8, same examples.
+__device__ __forceinline__ void mv_tile(const uint32_t (&whi)[kKSteps][4], const float4* __restrict__ wlo_lane,
+                                        const float* __restrict__ x_lane, float (&o)[4]) {
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < kKSteps; ++s) {
+    const float2 xv = *reinterpret_cast<const float2*>(x_lane + 8 * s);
+    const float4 lo = wlo_lane[s * 32];
+    const uint32_t bh0 = tf32_hi(xv.x), bh1 = tf32_hi(xv.y);
+    const uint32_t bl0 = __float_as_uint(xv.x - __uint_as_float(bh0)), bl1 = __float_as_uint(xv.y - __uint_as_float(bh1));
+    mma_tf32(d0, whi[s][0], whi[s][1], whi[s][2], whi[s][3], bh0, bh1);
+    mma_tf32(d1, __float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w), bh0, bh1);
+    mma_tf32(d2, whi[s][0], whi[s][1], whi[s][2], whi[s][3], bl0, bl1);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = d0[j] + (d1[j] + d2[j]);
+}
+
 // ---- shared-memory layout (float offsets) --------------------------------------------------------
 struct FwdSmem {
-  int hfull, qpfull, cvfull, xT, xV, P, KT, KV, qT, ch, qV, g, al, be, vT, vV, bc, len, bars, total;
+  int hfull, qpfull, cvfull, xT, xV, P, KT, KV, qT, ch, qV, g, al, be, vT, vV, bc, len, bars, wlo, total;
 };
 __host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond) {
   FwdSmem s{};
@@ -105,6 +141,7 @@ __host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond) {
   s.bc = take(kHS);
   s.len = take(kNB);
   s.bars = take(16);   // 5 mbarriers (8 bytes each)
+  s.wlo = take(15 * kKSteps * 32 * 4);   // W_lo fragments: [role warp][k-step][lane] float4
   s.total = o;
   return s;
 }
@@ -132,28 +169,40 @@ struct DecFwd3P {
 // Returns in o[0..3] the full dot products of row (2*rp + (ks>>1)) for examples 4*(ks&1)+m.
 __device__ __forceinline__ void mv_rowpair(const float4 (&w0)[7], const float4 (&w1)[7], const float* __restrict__ x,
                                            int ks, float (&o)[4]) {
-  float2 a0[kNB], a1[kNB];
+  // examples are processed in two blocks of 4 with 16 independent FFMA2 chains each: the
+  // dependent-issue latency of the packed FMA, not its throughput, bounds a 2-chain schedule
+  float r0[kNB], r1[kNB];
 #pragma unroll
-  for (int n = 0; n < kNB; ++n) a0[n] = a1[n] = make_float2(0.f, 0.f);
+  for (int nb4 = 0; nb4 < kNB; nb4 += 4) {
+    float2 a0l[4], a0h[4], a1l[4], a1h[4];
 #pragma unroll
-  for (int i = 0; i < 7; ++i) {
-    const int q = min(4 * i + ks, kH / 4 - 1);   // clamped quads carry zero weights
-    const float* xp = x + 4 * q;
+    for (int n = 0; n < 4; ++n) a0l[n] = a0h[n] = a1l[n] = a1h[n] = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int n = 0; n < kNB; ++n) {
-      const float4 xv = lds4(xp + n * kXS);
-      fma2(a0[n], lo2(w0[i]), lo2(xv));
-      fma2(a0[n], hi2(w0[i]), hi2(xv));
-      fma2(a1[n], lo2(w1[i]), lo2(xv));
-      fma2(a1[n], hi2(w1[i]), hi2(xv));
+    for (int i = 0; i < 7; ++i) {
+      const int q = min(4 * i + ks, kH / 4 - 1);   // clamped quads carry zero weights
+      const float* xp = x + nb4 * kXS + 4 * q;
+      float4 xv[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) xv[n] = lds4(xp + n * kXS);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        fma2(a0l[n], lo2(w0[i]), lo2(xv[n]));
+        fma2(a0h[n], hi2(w0[i]), hi2(xv[n]));
+        fma2(a1l[n], lo2(w1[i]), lo2(xv[n]));
+        fma2(a1h[n], hi2(w1[i]), hi2(xv[n]));
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      r0[nb4 + n] = (a0l[n].x + a0h[n].x) + (a0l[n].y + a0h[n].y);
+      r1[nb4 + n] = (a1l[n].x + a1h[n].x) + (a1l[n].y + a1h[n].y);
     }
   }
   const bool up = (ks & 2) != 0, odd = (ks & 1) != 0;
   float keep[kNB];
 #pragma unroll
   for (int n = 0; n < kNB; ++n) {
-    const float r0 = a0[n].x + a0[n].y, r1 = a1[n].x + a1[n].y;
-    const float mine = up ? r1 : r0, give = up ? r0 : r1;
+    const float mine = up ? r1[n] : r0[n], give = up ? r0[n] : r1[n];
     keep[n] = mine + __shfl_xor_sync(0xffffffffu, give, 2);
   }
 #pragma unroll
@@ -161,6 +210,36 @@ __device__ __forceinline__ void mv_rowpair(const float4 (&w0)[7], const float4 (
     const float mine = odd ? keep[4 + m] : keep[m], give = odd ? keep[m] : keep[4 + m];
     o[m] = mine + __shfl_xor_sync(0xffffffffu, give, 1);
   }
+}
+
+// 4-lane mat-vec tile, one row per thread: returns the dot products of the row for examples
+// 4*(ks>>1) + 2*(ks&1) + {0, 1}
+__device__ __forceinline__ void mv_row(const float4 (&w)[7], const float* __restrict__ x, int ks, float (&o)[2]) {
+  float2 al[kNB], ah[kNB];
+#pragma unroll
+  for (int n = 0; n < kNB; ++n) al[n] = ah[n] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const int q = min(4 * i + ks, kH / 4 - 1);
+    const float* xp = x + 4 * q;
+    float4 xv[kNB];
+#pragma unroll
+    for (int n = 0; n < kNB; ++n) xv[n] = lds4(xp + n * kXS);
+#pragma unroll
+    for (int n = 0; n < kNB; ++n) {
+      fma2(al[n], lo2(w[i]), lo2(xv[n]));
+      fma2(ah[n], hi2(w[i]), hi2(xv[n]));
+    }
+  }
+  float r[kNB];
+#pragma unroll
+  for (int n = 0; n < kNB; ++n) r[n] = (al[n].x + ah[n].x) + (al[n].y + ah[n].y);
+  const bool up = (ks & 2) != 0, odd = (ks & 1) != 0;
+  float k4[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) k4[m] = (up ? r[4 + m] : r[m]) + __shfl_xor_sync(0xffffffffu, up ? r[m] : r[4 + m], 2);
+#pragma unroll
+  for (int m = 0; m < 2; ++m) o[m] = (odd ? k4[2 + m] : k4[m]) + __shfl_xor_sync(0xffffffffu, odd ? k4[m] : k4[2 + m], 1);
 }
 
 // partial attention scores over this CTA's hidden slice: 4 lanes per (example, key) pair, 5 hidden
@@ -237,53 +316,55 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   const uint32_t rb_u = mapa_u32(smem_base, (uint32_t)(lane & 3)), rb_4 = rb[4];
   const uint32_t boff = (uint32_t)L.bars * 4u;
 
-  // ---- register-resident weights -----------------------------------------------------------------
-  const int ks = tid & 3, ks8 = tid & 7;
-  const bool actA = tid < 240, actC = COND && tid < 160, actD = tid >= 96;
-  float4 wA0[7], wA1[7], wD0[7], wD1[7], wC[4];
-  int lrA = 0;   // local output row of stage A owned after the butterfly
+  // ---- resident weight fragments; the content depends on the warp's role ---------------------------------
+  //   warps 0-7   stage A  tile w    of [q_T | W_c[:, :H] h (or q_V) | W_hh gates]   (120 rows, input h)
+  //   warps 8-12  stage D  tile w-8  of the 80 gate rows of W_ih[:, 2H:3H]            (input c_V)
+  //   warps 13-14 stage C  tile w-13 of W_qV (20 rows, conditional attention only)    (input q')
+  const int fg = lane >> 2, ft = lane & 3;   // fragment coordinates
+  const bool roleA = warp < 8, roleD = warp >= 8 && warp < 13, roleC = COND && (warp == 13 || warp == 14);
+  uint32_t whi[kKSteps][4];
+  float4* wlo_lane = reinterpret_cast<float4*>(smem + L.wlo) + (size_t)min(warp, 14) * kKSteps * 32 + lane;
+  int lr0 = 0;   // local output row of o[0], o[1]; o[2], o[3] belong to row lr0 + 8
   {
-    const int rp = tid >> 2;
+    const float *r0 = nullptr, *r1 = nullptr;
     auto rowA = [&](int lr) -> const float* {
+      if (lr >= 6 * kHS) return nullptr;
       const int type = lr / kHS, i = lr - type * kHS, hr = S0 + i;
       if (type == 0) return p.W_qT + (size_t)hr * kH;
       if (type == 1) return COND ? p.W_c + (size_t)hr * 2 * kH : p.W_qV + (size_t)hr * kH;
       return p.W_hh + (size_t)((type - 2) * kH + hr) * kH;
     };
-    const float* r0 = rowA(actA ? 2 * rp : 0);
-    const float* r1 = rowA(actA ? 2 * rp + 1 : 0);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const int q = 4 * i + ks;
-      const bool ok = actA && q < kH / 4;
-      wA0[i] = ok ? ldg4(r0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      wA1[i] = ok ? ldg4(r1 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    lrA = 2 * rp + (ks >> 1);
-    const int rpD = actD ? (tid - 96) >> 2 : 0;
     auto rowD = [&](int lr) -> const float* {
       const int g = lr / kHS, i = lr - g * kHS;
       return p.W_ih + (size_t)(g * kH + S0 + i) * 3 * kH + 2 * kH;
     };
-    const float* d0 = rowD(2 * rpD);
-    const float* d1 = rowD(2 * rpD + 1);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const int q = 4 * i + ks;
-      const bool ok = actD && q < kH / 4;
-      wD0[i] = ok ? ldg4(d0 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      wD1[i] = ok ? ldg4(d1 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    auto rowC = [&](int lr) -> const float* { return lr < kHS ? p.W_qV + (size_t)(S0 + lr) * kH : nullptr; };
+    if (roleA) {
+      lr0 = 16 * warp + fg;
+      r0 = rowA(lr0);
+      r1 = rowA(lr0 + 8);
+    } else if (roleD) {
+      lr0 = 16 * (warp - 8) + fg;
+      r0 = rowD(lr0);
+      r1 = rowD(lr0 + 8);
+    } else if (roleC) {
+      lr0 = 16 * (warp - 13) + fg;
+      r0 = rowC(lr0);
+      r1 = rowC(lr0 + 8);
     }
-    const int rC = actC ? tid >> 3 : 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int q = 8 * i + ks8;
-      const bool ok = actC && q < kH / 4;
-      wC[i] = ok ? ldg4(p.W_qV + (size_t)(S0 + rC) * kH + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < kKSteps; ++s) {
+      const int k = 8 * s + 2 * ft;
+      float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+      if (r0 && k < kH) a = __ldg(reinterpret_cast<const float2*>(r0 + k));
+      if (r1 && k < kH) b = __ldg(reinterpret_cast<const float2*>(r1 + k));
+      whi[s][0] = tf32_hi(a.x); whi[s][1] = tf32_hi(b.x); whi[s][2] = tf32_hi(a.y); whi[s][3] = tf32_hi(b.y);
+      if (warp < 15)
+        wlo_lane[s * 32] = make_float4(__uint_as_float(tf32_lo(a.x)), __uint_as_float(tf32_lo(b.x)),
+                                       __uint_as_float(tf32_lo(a.y)), __uint_as_float(tf32_lo(b.y)));
     }
   }
-  const int lrD = actD ? 2 * ((tid - 96) >> 2) + (ks >> 1) : 0;   // gate row owned after the stage-D butterfly
-  const int nA = 4 * (ks & 1);                                     // first example owned after a 4-lane butterfly
+  const int nF = 2 * ft;   // examples nF, nF + 1 are owned after a tile product
 
   // ---- one-time loads ------------------------------------------------------------------------------
   {
@@ -305,12 +386,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       const int n = nm / kM;
       KV_s[i] = (n < nb) ? __ldg(p.KV + ((size_t)b0 * kM + nm) * kH + S0 + h) : 0.f;
     }
-    for (int i = tid; i < kNB * kH; i += kThreads) {
-      const int n = i / kH, h = i - n * kH;
-      const float hv = (n < nb) ? __ldg(p.h_init + (size_t)(b0 + n) * kH + h) : 0.f;
-      hfull_s[n * kXS + h] = hv;
-      qpfull_s[n * kXS + h] = 0.f;
-      cvfull_s[n * kXS + h] = 0.f;
+    for (int i = tid; i < kNB * kXS; i += kThreads) {
+      const int n = i / kXS, h = i - n * kXS;
+      const float hv = (n < nb && h < kH) ? __ldg(p.h_init + (size_t)(b0 + n) * kH + h) : 0.f;
+      hfull_s[i] = hv;
+      qpfull_s[i] = 0.f;
+      cvfull_s[i] = 0.f;
       if (n < nb && h >= S0 && h < S0 + kHS) p.U[(size_t)(b0 + n) * H4 + kH + h] = hv;   // row group 0: h_{-1}
     }
     for (int i = tid; i < kNB * kGS; i += kThreads) g_s[i] = 0.f;
@@ -335,15 +416,19 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     }
   }
   float bs0 = 0.f, bs1 = 0.f;   // sum over steps of beta[warp][lane], beta[warp][lane + 32]
-  // Xe prefetch for the gate outputs this lane owns after the stage-A butterfly
-  const bool gateA = actA && lrA >= 2 * kHS;
-  const int xe_col = gateA ? ((lrA - 2 * kHS) / kHS) * kH + S0 + (lrA % kHS) : 0;
+  // Xe prefetch for the gate outputs this lane owns after its stage-A tile: rows lr0, lr0+8 x examples nF, nF+1
+  const bool gate0 = roleA && lr0 >= 2 * kHS && lr0 < 6 * kHS, gate1 = roleA && lr0 + 8 >= 2 * kHS && lr0 + 8 < 6 * kHS;
+  const int xe_col0 = gate0 ? ((lr0 - 2 * kHS) / kHS) * kH + S0 + (lr0 % kHS) : 0;
+  const int xe_col1 = gate1 ? ((lr0 + 8 - 2 * kHS) / kHS) * kH + S0 + ((lr0 + 8) % kHS) : 0;
   float xe[4] = {0.f, 0.f, 0.f, 0.f};
-  if (gateA) {
+  auto load_xe = [&](size_t rowbase) {
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
-      if (nA + m < nb) xe[m] = __ldg(p.Xe + (size_t)(b0 + nA + m) * H4 + xe_col);
-  }
+    for (int m = 0; m < 2; ++m) {
+      if (gate0 && nF + m < nb) xe[m] = __ldg(p.Xe + (rowbase + nF + m) * H4 + xe_col0);
+      if (gate1 && nF + m < nb) xe[2 + m] = __ldg(p.Xe + (rowbase + nF + m) * H4 + xe_col1);
+    }
+  };
+  load_xe((size_t)b0);
   // all CTAs of the cluster must have initialised their barriers and buffers before any remote store
   __syncthreads();
   cluster_barrier();
@@ -365,37 +450,31 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     }
     GSCAN3_STAMP(1);
     // ---- stage A: everything that depends only on h_{t-1} ---------------------------------------------
-    {
+    if (roleA) {
       float o[4];
-      mv_rowpair(wA0, wA1, hfull_s, ks, o);   // all lanes take part in the butterfly; idle ones carry zero weights
-      const int type = lrA / kHS, i = lrA - type * kHS;
-      if (actA) {
+      mv_tile(whi, wlo_lane, hfull_s + fg * kXS + 2 * ft, o);
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int n = nA + m;
+      for (int j = 0; j < 4; ++j) {
+        const int lr = lr0 + 8 * (j >> 1), n = nF + (j & 1);
+        const int type = lr / kHS, i = lr - type * kHS;
         if (type == 0) {
-          qT_s[n * kHS + i] = o[m];
-          if (n < nb) p.qT[(row0 + n) * kH + S0 + i] = o[m];
+          qT_s[n * kHS + i] = o[j];
+          if (n < nb) p.qT[(row0 + n) * kH + S0 + i] = o[j];
         } else if (type == 1) {
           if (COND) {
-            ch_s[n * kHS + i] = o[m];
+            ch_s[n * kHS + i] = o[j];
           } else {
-            qV_s[n * kHS + i] = o[m];
+            qV_s[n * kHS + i] = o[j];
             if (n < nb) {
-              p.qV[(row0 + n) * kH + S0 + i] = o[m];
+              p.qV[(row0 + n) * kH + S0 + i] = o[j];
               p.Qp[(row0 + n) * kH + S0 + i] = hfull_s[n * kXS + S0 + i];
             }
           }
-        } else {
-          g_s[n * kGS + lrA - 2 * kHS] = o[m] + xe[m];
+        } else if (type < 6) {
+          g_s[n * kGS + lr - 2 * kHS] = o[j] + xe[j];
         }
       }
-      }
-      if (gateA && t + 1 < p.T) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
-          if (nA + m < nb) xe[m] = __ldg(p.Xe + (row0 + B + nA + m) * H4 + xe_col);
-      }
+      if (t + 1 < p.T) load_xe(row0 + B);
     }
     __syncthreads();
     GSCAN3_STAMP(2);
@@ -404,8 +483,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(3);
     mbar_wait(bar0 + 8u * 0, par);
     GSCAN3_STAMP(4);
-    {
-      const int n = warp;   // kNB == number of warps
+    if (warp < kNB) {
+      const int n = warp;
       float s = -INFINITY;
       if (lane < Ti) {
         s = 0.f;
@@ -461,40 +540,17 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     if (COND) {
       mbar_wait(bar0 + 8u * 1, par);
       GSCAN3_STAMP(7);
-      if (actC) {
-        float2 acc[kNB];
+      if (roleC) {
+        float o[4];
+        mv_tile(whi, wlo_lane, qpfull_s + fg * kXS + 2 * ft, o);
 #pragma unroll
-        for (int n = 0; n < kNB; ++n) acc[n] = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int q = min(8 * i + ks8, kH / 4 - 1);
-#pragma unroll
-          for (int n = 0; n < kNB; ++n) {
-            const float4 xv = lds4(qpfull_s + n * kXS + 4 * q);
-            fma2(acc[n], lo2(wC[i]), lo2(xv));
-            fma2(acc[n], hi2(wC[i]), hi2(xv));
+        for (int j = 0; j < 4; ++j) {
+          const int r = lr0 + 8 * (j >> 1), n = nF + (j & 1);
+          if (r < kHS) {
+            qV_s[n * kHS + r] = o[j];
+            if (n < nb) p.qV[(row0 + n) * kH + S0 + r] = o[j];
           }
         }
-        // 8-lane halving butterfly: lane ks8 ends up with example n = ks8
-        float k4[4], k2[2];
-        {
-          const bool up = (ks8 & 4) != 0;
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const float lo = acc[m].x + acc[m].y, hi = acc[4 + m].x + acc[4 + m].y;
-            k4[m] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, up ? lo : hi, 4);
-          }
-        }
-        {
-          const bool up = (ks8 & 2) != 0;
-#pragma unroll
-          for (int m = 0; m < 2; ++m) k2[m] = (up ? k4[2 + m] : k4[m]) + __shfl_xor_sync(0xffffffffu, up ? k4[m] : k4[2 + m], 2);
-        }
-        const bool up = (ks8 & 1) != 0;
-        const float v = (up ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, up ? k2[0] : k2[1], 1);
-        const int r = tid >> 3, n = ks8;
-        qV_s[n * kHS + r] = v;
-        if (n < nb) p.qV[(row0 + n) * kH + S0 + r] = v;
       }
     }
     __syncthreads();
@@ -504,7 +560,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(9);
     mbar_wait(bar0 + 8u * 2, par);
     GSCAN3_STAMP(10);
-    {
+    if (warp < kNB) {
       const int n = warp;
       float s0 = 0.f, s1 = -INFINITY;
 #pragma unroll
@@ -559,11 +615,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     mbar_wait(bar0 + 8u * 3, par);
     GSCAN3_STAMP(12);
     // ---- stage D: c_V contribution to the gates, then the LSTM cell ---------------------------------------
-    if (actD) {
+    if (roleD) {
       float o[4];
-      mv_rowpair(wD0, wD1, cvfull_s, ks, o);
+      mv_tile(whi, wlo_lane, cvfull_s + fg * kXS + 2 * ft, o);
 #pragma unroll
-      for (int m = 0; m < 4; ++m) g_s[(nA + m) * kGS + lrD] += o[m];
+      for (int j = 0; j < 4; ++j) g_s[(nF + (j & 1)) * kGS + lr0 + 8 * (j >> 1)] += o[j];
     }
     __syncthreads();
     GSCAN3_STAMP(13);
