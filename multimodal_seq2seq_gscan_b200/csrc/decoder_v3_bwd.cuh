@@ -1,0 +1,611 @@
+// Decoder backward sweep, version 3 (BPTT of seq2seq_model.py:359-428, reverse time; recipe:
+// SURVEY.md A.6 / oracle/manual_backward.py stage B4).  Same organisation as the forward sweep in
+// decoder_v3.cuh: a cluster of 5 CTAs owns 8 examples, CTA r owns the hidden slice [20r, 20r+20) of
+// every H-sized gradient, CTAs exchange with st.async + mbarrier, mat-vecs run on mma.sync 3xTF32.
+//
+// The transposed products are INPUT-sliced: CTA r multiplies its own slice of da / dd / dq_V / dq_T
+// by the matching columns of W^T and the partial results are reduce-scattered to the owners
+//     X_e  partial dc_V   = W_ih[:, 2H:3H]^T da          [8][100] -> owners
+//     X_a  partial dbeta  = dc_V . K^V_m over the slice  [8][36]  -> all
+//     X_b  partial dq'    = W_qV^T dq_V                  [8][100] -> owners
+//     X_c  partial dalpha (through P_j = W K^T_j)        [8][Ti]  -> all
+//     X_d  partial dh     = W_hh^T da + W_c[:, :H]^T dd + W_qT^T dq_T   [8][100] -> owners
+// What does not have to be inside the recurrence is left to batched kernels after the sweep: the
+// "value path" of both attentions, dK_m += w_m dc (dc_T, dc_V are linear in the saved da, dd, dU).
+#pragma once
+#include "decoder_v3.cuh"
+
+namespace gscan {
+namespace v3 {
+
+constexpr int kDaS = 88;    // row stride of da_s (80 gate pre-activation gradients + pad)
+constexpr int kVs = 24;     // row stride of the 20-wide mma B operands (dq_V, dd, dq_T); pad stays zero
+constexpr int kTiles = 7;   // ceil(100 / 16) output tiles of the transposed products
+// weight units (16 rows x 8 columns each) per output tile, in shared memory fragment order
+constexpr int kUcV = 0, kUhh = 10, kUc = 20, kUqT = 23, kUqV = 26, kUnitsPerTile = 29;
+constexpr int kMaxTiB = 16;   // text positions per attention thread: 8 registers
+
+struct BwdSmem {
+  int W, KV, KT, P, da, dqV, dd, dqT, dUcT, dhpart, dcV, xcV, xbe, xqp, xal, xdh, drV, drT, a1, vT, vV, len, bars, total;
+};
+__host__ __device__ inline BwdSmem bwd_smem(int Ti, int cond) {
+  BwdSmem s{};
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  const int RBl = kHS * (4 + cond);
+  s.W = take(kTiles * kUnitsPerTile * 32 * 4);
+  s.KV = take(kNB * kM * kHS);
+  s.KT = take(kNB * Ti * kHS);
+  s.P = take(kNB * Ti * RBl);
+  s.da = take(kNB * kDaS);
+  s.dqV = take(kNB * kVs);
+  s.dd = take(kNB * kVs);
+  s.dqT = take(kNB * kVs);
+  s.dUcT = take(kNB * kHS);
+  s.dhpart = take(kNB * kH);
+  s.dcV = take(kNB * kHS);
+  s.xcV = take(kC * kNB * kHS);
+  s.xbe = take(kC * kNB * kM);
+  s.xqp = take(kC * kNB * kHS);
+  s.xal = take(kC * kNB * Ti);
+  s.xdh = take(kC * kNB * kHS);
+  s.drV = take(kNB * kM);
+  s.drT = take(kNB * Ti);
+  s.a1 = take(kNB * Ti);
+  s.vT = take(kHS);
+  s.vV = take(kHS);
+  s.len = take(kNB);
+  s.bars = take(16);
+  s.total = o;
+  return s;
+}
+
+struct DecBwd3P {
+  int B, T, Ti;
+  const float *W_ih, *W_hh, *W_qV, *W_c, *W_qT;   // original row-major parameters
+  const float* PT;                                // [Ti][B][RB] (see DecFwd3P)
+  const float *vT, *vV;
+  const float *KT, *KV;
+  const int* cmd_len;
+  const float *Cs, *gates, *alpha, *beta, *Qp, *qT, *qV;   // saved by the forward sweep
+  const float* dU;          // [T][B][4H] gradient of [e | h | c_T | c_V] from the output projection
+  const float* dbeta_aux;   // [B][M] or null
+  float *dgates, *dd, *dqV, *dqT;   // [T][B][4H], [T][B][H] x3: operands of the weight-gradient GEMMs
+  float *dKT, *dKV;         // key-path part only; the value path is added after the sweep
+  float* dh0;               // [B][H]
+  float *dvT, *dvV;         // [H] each, atomically accumulated (zeroed by the host)
+  long long* timeline;
+};
+
+// o = W_tile[16 x 8*NSTEPS] . x^T: fp32 fragments from shared memory, split into tf32 hi/lo on the fly
+template <int NSTEPS>
+__device__ __forceinline__ void mv_units(const float4* __restrict__ w_lane, const float* __restrict__ x_lane,
+                                         float (&o)[4]) {
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < NSTEPS; ++s) {
+    const float2 xv = *reinterpret_cast<const float2*>(x_lane + 8 * s);
+    const float4 a = w_lane[s * 32];
+    const uint32_t ah0 = tf32_hi(a.x), ah1 = tf32_hi(a.y), ah2 = tf32_hi(a.z), ah3 = tf32_hi(a.w);
+    const uint32_t al0 = __float_as_uint(a.x - __uint_as_float(ah0)), al1 = __float_as_uint(a.y - __uint_as_float(ah1)),
+                   al2 = __float_as_uint(a.z - __uint_as_float(ah2)), al3 = __float_as_uint(a.w - __uint_as_float(ah3));
+    const uint32_t bh0 = tf32_hi(xv.x), bh1 = tf32_hi(xv.y);
+    const uint32_t bl0 = __float_as_uint(xv.x - __uint_as_float(bh0)), bl1 = __float_as_uint(xv.y - __uint_as_float(bh1));
+    mma_tf32(d0, ah0, ah1, ah2, ah3, bh0, bh1);
+    mma_tf32(d1, al0, al1, al2, al3, bh0, bh1);
+    mma_tf32(d2, ah0, ah1, ah2, ah3, bl0, bl1);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = d0[j] + (d1[j] + d2[j]);
+}
+
+template <bool COND>
+__global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bwd_v3_kernel(DecBwd3P p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int RBl = kHS * (4 + (COND ? 1 : 0));
+  constexpr int COFF = COND ? kHS : 0;   // first gate column of a P row
+  constexpr int H4 = 4 * kH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int B = p.B, Ti = p.Ti;
+  const int b0 = (blockIdx.x / kC) * kNB;
+  const int nb = min(kNB, B - b0);
+  const int S0 = rank * kHS;
+  const BwdSmem L = bwd_smem(Ti, COND ? 1 : 0);
+
+  float4* W_s = reinterpret_cast<float4*>(smem + L.W);
+  float* KV_s = smem + L.KV;
+  float* KT_s = smem + L.KT;
+  float* P_s = smem + L.P;
+  float* da_s = smem + L.da;
+  float* dqV_s = smem + L.dqV;
+  float* dd_s = smem + L.dd;
+  float* dqT_s = smem + L.dqT;
+  float* dUcT_s = smem + L.dUcT;
+  float* dhpart_s = smem + L.dhpart;
+  float* dcV_s = smem + L.dcV;
+  float* xcV_s = smem + L.xcV;
+  float* xbe_s = smem + L.xbe;
+  float* xqp_s = smem + L.xqp;
+  float* xal_s = smem + L.xal;
+  float* xdh_s = smem + L.xdh;
+  float* drV_s = smem + L.drV;
+  float* drT_s = smem + L.drT;
+  float* a1_s = smem + L.a1;
+  float* vT_s = smem + L.vT;
+  float* vV_s = smem + L.vV;
+  int* len_s = reinterpret_cast<int*>(smem + L.len);
+
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t boff = (uint32_t)L.bars * 4u;
+  const uint32_t bar0 = smem_base + boff;   // [0] X_e  [1] X_a  [2] X_b  [3] X_c  [4] X_d
+  uint32_t rb[kC];
+#pragma unroll
+  for (int d = 0; d < kC; ++d) rb[d] = mapa_u32(smem_base, (uint32_t)d);
+  const uint32_t rb_u = mapa_u32(smem_base, (uint32_t)(lane & 3)), rb_4 = rb[4];
+
+  // ---- one-time staging ------------------------------------------------------------------------------
+  // transposed weight slices as mma A fragments: unit (tile, step) holds rows h = 16*tile + {g, g+8},
+  // columns k = 8*step + {2t, 2t+1} of A[h][k] = W[input k of this CTA's slice][output h]
+  for (int idx = tid; idx < kTiles * kUnitsPerTile * 32; idx += kThreads) {
+    const int ln = idx & 31, unit = idx >> 5;
+    const int tile = unit / kUnitsPerTile, u = unit - tile * kUnitsPerTile;
+    const int g = ln >> 2, tt = ln & 3;
+    auto A = [&](int h, int kk) -> float {
+      if (h >= kH) return 0.f;
+      if (u < kUc) {   // inputs: the 80 gate pre-activation gradients of the slice
+        const int k = 8 * (u < kUhh ? u - kUcV : u - kUhh) + kk;
+        const int gk = k / kHS, ik = k - gk * kHS;
+        const size_t row = (size_t)gk * kH + S0 + ik;
+        return u < kUhh ? __ldg(p.W_ih + row * 3 * kH + 2 * kH + h) : __ldg(p.W_hh + row * kH + h);
+      }
+      const int grp = (u - kUc) / 3;
+      const int k = 8 * ((u - kUc) - 3 * grp) + kk;
+      if (k >= kHS) return 0.f;
+      if (grp == 0) return COND ? __ldg(p.W_c + (size_t)(S0 + k) * 2 * kH + h) : 0.f;
+      if (grp == 1) return __ldg(p.W_qT + (size_t)(S0 + k) * kH + h);
+      return __ldg(p.W_qV + (size_t)(S0 + k) * kH + h);
+    };
+    const int h0 = 16 * tile + g;
+    W_s[idx] = make_float4(A(h0, 2 * tt), A(h0 + 8, 2 * tt), A(h0, 2 * tt + 1), A(h0 + 8, 2 * tt + 1));
+  }
+  {
+    constexpr int RB = kH * (4 + (COND ? 1 : 0));
+    for (int i = tid; i < kNB * Ti * RBl; i += kThreads) {
+      const int col = i % RBl, nj = i / RBl;
+      const int j = nj % Ti, n = nj / Ti;
+      const int type = col / kHS, ii = col - type * kHS;
+      P_s[i] = (n < nb) ? __ldg(p.PT + ((size_t)j * B + b0 + n) * RB + type * kH + S0 + ii) : 0.f;
+    }
+    for (int i = tid; i < kNB * Ti * kHS; i += kThreads) {
+      const int h = i % kHS, nj = i / kHS;
+      const int j = nj % Ti, n = nj / Ti;
+      KT_s[i] = (n < nb) ? __ldg(p.KT + ((size_t)j * B + b0 + n) * kH + S0 + h) : 0.f;
+    }
+    for (int i = tid; i < kNB * kM * kHS; i += kThreads) {
+      const int h = i % kHS, nm = i / kHS;
+      const int n = nm / kM;
+      KV_s[i] = (n < nb) ? __ldg(p.KV + ((size_t)b0 * kM + nm) * kH + S0 + h) : 0.f;
+    }
+    for (int i = tid; i < kNB * kDaS; i += kThreads) da_s[i] = 0.f;
+    for (int i = tid; i < kNB * kVs; i += kThreads) { dqV_s[i] = 0.f; dd_s[i] = 0.f; dqT_s[i] = 0.f; }
+    for (int i = tid; i < kNB * kH; i += kThreads) dhpart_s[i] = 0.f;
+    if (tid < kHS) {
+      vT_s[tid] = __ldg(p.vT + S0 + tid);
+      vV_s[tid] = __ldg(p.vV + S0 + tid);
+    }
+    if (tid < kNB) len_s[tid] = (tid < nb) ? max(1, min(p.cmd_len[b0 + tid], Ti)) : 1;
+    if (tid == 0) {
+      for (int k = 0; k < 5; ++k) mbar_init(bar0 + 8u * k, 1);
+      fence_mbar_init();
+    }
+  }
+
+  // ---- thread roles ------------------------------------------------------------------------------------
+  const int fg = lane >> 2, ft = lane & 3, nF = 2 * ft;   // mma fragment coordinates
+  const bool cellT = tid < kNB * kHS;                     // (example cn, hidden S0 + chh)
+  const int cn = tid / kHS, chh = tid - cn * kHS;
+  const bool attT = tid < 2 * kNB * kHS;                  // (example an, hidden S0 + ah), keys 2k + mg
+  const int an = attT ? (tid >> 1) / kHS : 0, ah = attT ? (tid >> 1) % kHS : 0, mg = tid & 1;
+  const bool an_ok = attT && an < nb;
+  const bool cn_ok = cellT && cn < nb;
+
+  // attention accumulators, thread-private for the whole sweep
+  float dKV_acc[kM / 2], dKT_acc[kMaxTiB / 2], dvV_acc = 0.f, dvT_acc = 0.f;
+#pragma unroll
+  for (int k = 0; k < kM / 2; ++k) dKV_acc[k] = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxTiB / 2; ++k) dKT_acc[k] = 0.f;
+  const float my_vV = attT ? __ldg(p.vV + S0 + ah) : 0.f, my_vT = attT ? __ldg(p.vT + S0 + ah) : 0.f;
+
+  // recurrent state of the cell threads
+  float dc_carry = 0.f, dh_extra = 0.f;
+  // prefetched saved activations of the step about to be processed
+  float c_gi = 0.f, c_gf = 0.f, c_gg = 0.f, c_go = 0.f, c_cprev = 0.f, c_cnew = 0.f, c_dUh = 0.f, c_dUcT = 0.f,
+        c_dUcV = 0.f, c_qp = 0.f;
+  float a_qv = 0.f, a_qt = 0.f;
+  float s_b0 = 0.f, s_b1 = 0.f, s_al = 0.f, s_aux0 = 0.f, s_aux1 = 0.f;
+  auto load_cell = [&](int t, bool first) {
+    if (!cn_ok) return;
+    const size_t row = (size_t)t * B + b0 + cn;
+    const float* gp = p.gates + row * H4 + S0 + chh;
+    c_gi = __ldg(gp); c_gf = __ldg(gp + kH); c_gg = __ldg(gp + 2 * kH); c_go = __ldg(gp + 3 * kH);
+    c_cnew = first ? __ldg(p.Cs + (row + B) * kH + S0 + chh) : c_cprev;
+    c_cprev = __ldg(p.Cs + row * kH + S0 + chh);
+    const float* du = p.dU + row * H4 + S0 + chh;
+    c_dUh = __ldg(du + kH); c_dUcT = __ldg(du + 2 * kH); c_dUcV = __ldg(du + 3 * kH);
+    if (COND) c_qp = __ldg(p.Qp + row * kH + S0 + chh);
+  };
+  auto load_att = [&](int t) {
+    if (!an_ok) return;
+    const size_t row = (size_t)t * B + b0 + an;
+    a_qv = __ldg(p.qV + row * kH + S0 + ah);
+    a_qt = __ldg(p.qT + row * kH + S0 + ah);
+  };
+  auto load_soft = [&](int t) {
+    if (warp >= nb) return;
+    const size_t row = (size_t)t * B + b0 + warp;
+    s_b0 = __ldg(p.beta + row * kM + lane);
+    s_b1 = (lane < kM - 32) ? __ldg(p.beta + row * kM + 32 + lane) : 0.f;
+    s_al = (lane < Ti) ? __ldg(p.alpha + row * Ti + lane) : 0.f;
+  };
+  load_cell(p.T - 1, true);
+  load_att(p.T - 1);
+  load_soft(p.T - 1);
+  if (p.dbeta_aux && warp < nb) {
+    s_aux0 = __ldg(p.dbeta_aux + (size_t)(b0 + warp) * kM + lane);
+    s_aux1 = (lane < kM - 32) ? __ldg(p.dbeta_aux + (size_t)(b0 + warp) * kM + 32 + lane) : 0.f;
+  }
+  __syncthreads();
+  cluster_barrier();
+
+  const uint32_t bytes_vec = (uint32_t)(kC * kNB * kHS * 4), bytes_be = (uint32_t)(kC * kNB * kM * 4),
+                 bytes_al = (uint32_t)(kC * kNB * Ti * 4);
+  const float4* w_tile = W_s + (size_t)(warp < kTiles ? warp : (warp < 2 * kTiles ? warp - kTiles : 0)) * kUnitsPerTile * 32 + lane;
+  const int tile = warp < kTiles ? warp : warp - kTiles;
+
+  // send the four values of a tile result to the owners of their hidden rows (reduce-scatter)
+  auto scatter_tile = [&](const float (&o)[4], int xoff, uint32_t bar) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int h = 16 * tile + fg + 8 * (j >> 1), n = nF + (j & 1);
+      if (h < kH) {
+        const int owner = h / kHS, hh = h - owner * kHS;
+        const uint32_t dst = mapa_u32(smem_base, (uint32_t)owner);
+        st_async_f32(dst + (uint32_t)(xoff + (rank * kNB + n) * kHS + hh) * 4u, o[j], dst + boff + 8u * bar);
+      }
+    }
+  };
+
+  int it = 0;
+  for (int t = p.T - 1; t >= 0; --t, ++it) {
+    const size_t row0 = (size_t)t * B + b0;
+    const uint32_t par = (uint32_t)(it & 1);
+    GSCAN3_STAMP(0);
+    // ---- tanh of both attentions for this step: depends only on saved activations, overlaps the X_d wait ----
+    float zV[kM / 2], zT[kMaxTiB / 2];
+    if (attT) {
+#pragma unroll
+      for (int k = 0; k < kM / 2; ++k) zV[k] = act_tanh(a_qv + KV_s[(an * kM + 2 * k + mg) * kHS + ah]);
+#pragma unroll
+      for (int k = 0; k < kMaxTiB / 2; ++k) {
+        const int j = 2 * k + mg;
+        zT[k] = (j < Ti) ? act_tanh(a_qt + KT_s[(an * Ti + j) * kHS + ah]) : 0.f;
+      }
+      if (t > 0) load_att(t - 1);
+    }
+    GSCAN3_STAMP(1);
+    if (it > 0) mbar_wait(bar0 + 8u * 4, par ^ 1u);   // dh partials of the previous iteration (X_d)
+    if (tid == 0) {
+      mbar_arm(bar0 + 8u * 0, bytes_vec);
+      mbar_arm(bar0 + 8u * 1, bytes_be);
+      mbar_arm(bar0 + 8u * 2, bytes_vec);
+      mbar_arm(bar0 + 8u * 3, bytes_al);
+      mbar_arm(bar0 + 8u * 4, bytes_vec);
+    }
+    GSCAN3_STAMP(2);
+    // ---- B1: LSTM cell backward ------------------------------------------------------------------------
+    if (cellT) {
+      float dh_t = dh_extra + c_dUh;
+      if (it > 0) {
+#pragma unroll
+        for (int r = 0; r < kC; ++r) dh_t += xdh_s[(r * kNB + cn) * kHS + chh];
+      }
+      const float tc = act_tanh(c_cnew);
+      const float d_o = dh_t * tc;
+      const float dc_t = fmaf(dh_t * c_go, 1.f - tc * tc, dc_carry);
+      const float da0 = dc_t * c_gg * c_gi * (1.f - c_gi);
+      const float da1 = dc_t * c_cprev * c_gf * (1.f - c_gf);
+      const float da2 = dc_t * c_gi * (1.f - c_gg * c_gg);
+      const float da3 = d_o * c_go * (1.f - c_go);
+      dc_carry = dc_t * c_gf;
+      float* dp = da_s + cn * kDaS + chh;
+      dp[0] = da0; dp[kHS] = da1; dp[2 * kHS] = da2; dp[3 * kHS] = da3;
+      dUcT_s[cn * kHS + chh] = c_dUcT;
+      if (cn_ok) {
+        float* dg = p.dgates + (row0 + cn) * H4 + S0 + chh;
+        dg[0] = da0; dg[kH] = da1; dg[2 * kH] = da2; dg[3 * kH] = da3;
+      }
+    }
+    __syncthreads();
+    GSCAN3_STAMP(3);
+    // ---- B2: partial dc_V (X_e) and the W_hh^T da piece of dh ----------------------------------------------
+    if (warp < kTiles) {
+      float o[4];
+      mv_units<10>(w_tile + kUcV * 32, da_s + fg * kDaS + 2 * ft, o);
+      scatter_tile(o, L.xcV, 0);
+    } else if (warp < 2 * kTiles) {
+      float o[4];
+      mv_units<10>(w_tile + kUhh * 32, da_s + fg * kDaS + 2 * ft, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int h = 16 * tile + fg + 8 * (j >> 1);
+        if (h < kH) dhpart_s[(nF + (j & 1)) * kH + h] = o[j];
+      }
+    }
+    GSCAN3_STAMP(4);
+    // ---- B3: the part of dalpha that does not depend on dd: da . P_gates + dU_cT . K^T --------------------------
+    {
+      const int total = kNB * Ti * 4;
+      for (int base = warp * 32; base < total; base += kThreads) {
+        const int item = base + lane, pair = item >> 2, u = item & 3;
+        float s = 0.f;
+        if (item < total) {
+          const int n = pair / Ti;
+          const float* pp = P_s + (size_t)pair * RBl + COFF + 20 * u;
+          const float* dp = da_s + n * kDaS + 20 * u;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const float4 a = lds4(dp + 4 * i), b = lds4(pp + 4 * i);
+            s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+          }
+          const float* kp = KT_s + (size_t)pair * kHS + 5 * u;
+          const float* up = dUcT_s + n * kHS + 5 * u;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) s = fmaf(up[i], kp[i], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (item < total) {
+          if (COND) {
+            if (u == 0) a1_s[pair] = s;
+          } else {   // nothing else contributes: this is already the partial dalpha (X_c)
+            const uint32_t off = (uint32_t)(L.xal + rank * kNB * Ti + pair) * 4u;
+            st_async_f32(rb_u + off, s, rb_u + boff + 8u * 3);
+            if (u == 0) st_async_f32(rb_4 + off, s, rb_4 + boff + 8u * 3);
+          }
+        }
+      }
+    }
+    GSCAN3_STAMP(5);
+    // ---- B4: dc_V slice assembled, partial dbeta over the slice (X_a) ---------------------------------------------
+    mbar_wait(bar0 + 8u * 0, par);
+    if (cellT) {
+      float v = c_dUcV;
+#pragma unroll
+      for (int r = 0; r < kC; ++r) v += xcV_s[(r * kNB + cn) * kHS + chh];
+      dcV_s[cn * kHS + chh] = v;
+    }
+    __syncthreads();
+    GSCAN3_STAMP(6);
+    {
+      const int u = lane & 3;
+      constexpr int total = kNB * kM * 4;
+      for (int base = warp * 32; base < total; base += kThreads) {
+        const int item = base + lane, pair = item >> 2;
+        float s = 0.f;
+        if (item < total) {
+          const int n = pair / kM;
+          const float* kp = KV_s + pair * kHS + 5 * u;
+          const float* dp = dcV_s + n * kHS + 5 * u;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) s = fmaf(dp[i], kp[i], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (item < total) {
+          const uint32_t off = (uint32_t)(L.xbe + rank * kNB * kM + pair) * 4u;
+          st_async_f32(rb_u + off, s, rb_u + boff + 8u * 1);
+          if (u == 0) st_async_f32(rb_4 + off, s, rb_4 + boff + 8u * 1);
+        }
+      }
+    }
+    GSCAN3_STAMP(7);
+    // ---- B5: softmax backward of the visual attention ---------------------------------------------------------------
+    mbar_wait(bar0 + 8u * 1, par);
+    if (warp < kNB) {
+      const int n = warp;
+      float d0 = s_aux0, d1 = s_aux1;
+#pragma unroll
+      for (int r = 0; r < kC; ++r) d0 += xbe_s[(r * kNB + n) * kM + lane];
+      if (lane < kM - 32) {
+#pragma unroll
+        for (int r = 0; r < kC; ++r) d1 += xbe_s[(r * kNB + n) * kM + 32 + lane];
+      }
+      const float dot = warp_sum(fmaf(s_b0, d0, s_b1 * d1));
+      drV_s[n * kM + lane] = s_b0 * (d0 - dot);
+      if (lane < kM - 32) drV_s[n * kM + 32 + lane] = s_b1 * (d1 - dot);
+    }
+    __syncthreads();
+    GSCAN3_STAMP(8);
+    // ---- B6: key path of the visual attention: dK^V, dq_V, dv_V ---------------------------------------------------------
+    if (attT) {
+      float dq = 0.f;
+#pragma unroll
+      for (int k = 0; k < kM / 2; ++k) {
+        const float dr = drV_s[an * kM + 2 * k + mg];
+        const float z = zV[k];
+        const float g = dr * my_vV * (1.f - z * z);
+        dKV_acc[k] += g;
+        dq += g;
+        dvV_acc = fmaf(dr, z, dvV_acc);
+      }
+      dq += __shfl_xor_sync(0xffffffffu, dq, 1);
+      if (mg == 0) {
+        dqV_s[an * kVs + ah] = dq;
+        if (an_ok) p.dqV[(row0 + an) * kH + S0 + ah] = dq;
+      }
+    }
+    __syncthreads();
+    GSCAN3_STAMP(9);
+    // ---- B7: partial dq' = W_qV^T dq_V (X_b) ------------------------------------------------------------------------------
+    if (warp < kTiles) {
+      float o[4];
+      mv_units<3>(w_tile + kUqV * 32, dqV_s + fg * kVs + 2 * ft, o);
+      scatter_tile(o, L.xqp, 2);
+    }
+    GSCAN3_STAMP(10);
+    mbar_wait(bar0 + 8u * 2, par);
+    if (cellT) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < kC; ++r) v += xqp_s[(r * kNB + cn) * kHS + chh];
+      if (COND) {
+        const float d = v * (1.f - c_qp * c_qp);
+        dd_s[cn * kVs + chh] = d;
+        if (cn_ok) p.dd[(row0 + cn) * kH + S0 + chh] = d;
+      } else {
+        dh_extra = v;   // q' = h_{t-1}: joins dh at the next cell backward
+      }
+      if (t > 0) load_cell(t - 1, false);
+    }
+    GSCAN3_STAMP(11);
+    if (COND) {
+      __syncthreads();
+      // ---- B9: the W_c[:, :H]^T dd piece of dh, and the partial dalpha completed with dd . P_cond (X_c) -------------
+      if (warp >= kTiles && warp < 2 * kTiles) {
+        float o[4];
+        mv_units<3>(w_tile + kUc * 32, dd_s + fg * kVs + 2 * ft, o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int h = 16 * tile + fg + 8 * (j >> 1);
+          if (h < kH) dhpart_s[(nF + (j & 1)) * kH + h] += o[j];
+        }
+      } else {
+        // warps 0-6 and 14-15: 9 warps, 4 lanes per (example, position) pair
+        const int w9 = warp < kTiles ? warp : warp - kTiles;
+        const int total = kNB * Ti * 4;
+        for (int base = w9 * 32; base < total; base += 9 * 32) {
+          const int item = base + lane, pair = item >> 2, u = item & 3;
+          float s = 0.f;
+          if (item < total) {
+            const int n = pair / Ti;
+            const float* pp = P_s + (size_t)pair * RBl + 5 * u;
+            const float* dp = dd_s + n * kVs + 5 * u;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) s = fmaf(dp[i], pp[i], s);
+            if (u == 0) s += a1_s[pair];
+          }
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          if (item < total) {
+            const uint32_t off = (uint32_t)(L.xal + rank * kNB * Ti + pair) * 4u;
+            st_async_f32(rb_u + off, s, rb_u + boff + 8u * 3);
+            if (u == 0) st_async_f32(rb_4 + off, s, rb_4 + boff + 8u * 3);
+          }
+        }
+      }
+    }
+    GSCAN3_STAMP(12);
+    // ---- B10: softmax backward of the textual attention ---------------------------------------------------------------------
+    mbar_wait(bar0 + 8u * 3, par);
+    if (warp < kNB) {
+      const int n = warp;
+      float d = 0.f;
+      if (lane < Ti) {
+#pragma unroll
+        for (int r = 0; r < kC; ++r) d += xal_s[(r * kNB + n) * Ti + lane];
+      }
+      const float dot = warp_sum(s_al * d);   // alpha is zero at masked positions and beyond Ti
+      if (lane < Ti) drT_s[n * Ti + lane] = s_al * (d - dot);
+      if (t > 0) load_soft(t - 1);
+    }
+    __syncthreads();
+    GSCAN3_STAMP(13);
+    // ---- B11: key path of the textual attention: dK^T, dq_T, dv_T ---------------------------------------------------------------
+    if (attT) {
+      float dq = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxTiB / 2; ++k) {
+        const int j = 2 * k + mg;
+        if (j < Ti) {
+          const float dr = drT_s[an * Ti + j];
+          const float z = zT[k];
+          const float g = dr * my_vT * (1.f - z * z);
+          dKT_acc[k] += g;
+          dq += g;
+          dvT_acc = fmaf(dr, z, dvT_acc);
+        }
+      }
+      dq += __shfl_xor_sync(0xffffffffu, dq, 1);
+      if (mg == 0) {
+        dqT_s[an * kVs + ah] = dq;
+        if (an_ok) p.dqT[(row0 + an) * kH + S0 + ah] = dq;
+      }
+    }
+    __syncthreads();
+    GSCAN3_STAMP(14);
+    // ---- B12: last piece of dh, W_qT^T dq_T, added to the earlier pieces and reduce-scattered (X_d) ------------------------------
+    if (warp < kTiles) {
+      float o[4];
+      mv_units<3>(w_tile + kUqT * 32, dqT_s + fg * kVs + 2 * ft, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int h = 16 * tile + fg + 8 * (j >> 1);
+        if (h < kH) o[j] += dhpart_s[(nF + (j & 1)) * kH + h];
+      }
+      scatter_tile(o, L.xdh, 4);
+    }
+    GSCAN3_STAMP(15);
+  }
+
+  // ---- epilogue -------------------------------------------------------------------------------------------
+  mbar_wait(bar0 + 8u * 4, (uint32_t)((it - 1) & 1));
+  if (cn_ok) {
+    float dh = dh_extra;
+#pragma unroll
+    for (int r = 0; r < kC; ++r) dh += xdh_s[(r * kNB + cn) * kHS + chh];
+    p.dh0[(size_t)(b0 + cn) * kH + S0 + chh] = dh + dc_carry;   // h_{-1} = c_{-1} = the same tensor
+  }
+  if (an_ok) {
+#pragma unroll
+    for (int k = 0; k < kM / 2; ++k) p.dKV[((size_t)(b0 + an) * kM + 2 * k + mg) * kH + S0 + ah] = dKV_acc[k];
+#pragma unroll
+    for (int k = 0; k < kMaxTiB / 2; ++k) {
+      const int j = 2 * k + mg;
+      if (j < Ti) p.dKT[((size_t)j * B + b0 + an) * kH + S0 + ah] = dKT_acc[k];
+    }
+    atomicAdd(p.dvV + S0 + ah, dvV_acc);
+    atomicAdd(p.dvT + S0 + ah, dvT_acc);
+  }
+  cluster_barrier();
+}
+
+// ---- after the sweep: value path of both attentions ------------------------------------------------------
+//   dK^V[b, m, :] += sum_t beta[t, b, m]  * dc_V[t, b, :]
+//   dK^T[j, b, :] += sum_t alpha[t, b, j] * dc_T[t, b, :]
+// with dc = [dc_T | dc_V] rows of width 2H at stride ldc.  grid = (B, 2): y = 0 visual, y = 1 textual.
+__global__ void __launch_bounds__(256) attn_value_bwd_kernel(const float* __restrict__ dc, long ldc, const float* __restrict__ beta,
+                                                             const float* __restrict__ alpha, int B, int T, int Ti, int M, int H,
+                                                             float* __restrict__ dKV, float* __restrict__ dKT) {
+  extern __shared__ float w_s[];   // [T][N] attention weights of this example
+  const int b = blockIdx.x, vis = blockIdx.y == 0;
+  const int N = vis ? M : Ti;
+  const float* w = vis ? beta : alpha;
+  for (int i = threadIdx.x; i < T * N; i += blockDim.x) {
+    const int t = i / N, k = i - t * N;
+    w_s[i] = __ldg(w + ((size_t)t * B + b) * N + k);
+  }
+  __syncthreads();
+  const float* dcb = dc + (vis ? H : 0);
+  for (int o = threadIdx.x; o < N * H; o += blockDim.x) {
+    const int k = o / H, h = o - k * H;
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc = fmaf(w_s[t * N + k], __ldg(dcb + ((size_t)t * B + b) * ldc + h), acc);
+    if (vis) dKV[((size_t)b * M + k) * H + h] += acc;
+    else dKT[((size_t)k * B + b) * H + h] += acc;
+  }
+}
+
+}  // namespace v3
+}  // namespace gscan

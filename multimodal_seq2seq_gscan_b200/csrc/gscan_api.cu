@@ -14,6 +14,7 @@
 #include "recurrent.cuh"
 #include "decoder_cluster.cuh"
 #include "decoder_v3.cuh"
+#include "decoder_v3_bwd.cuh"
 
 using namespace gscan;
 
@@ -592,6 +593,65 @@ int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, con
   return 0;
 }
 
+template <bool COND>
+int v3_bwd_prepare(size_t bytes) {
+  static bool done = false, ok = false;
+  static size_t done_bytes = 0;
+  if (done && bytes <= done_bytes) return ok ? 0 : GSCAN_E_UNSUPPORTED;
+  auto kern = v3::dec_bwd_v3_kernel<COND>;
+  ok = false;
+  done = true;
+  done_bytes = bytes;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return GSCAN_E_UNSUPPORTED;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(v3::kC);
+  cfg.blockDim = dim3(v3::kThreads);
+  cfg.dynamicSmemBytes = bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = v3::kC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+    cudaGetLastError();
+    return GSCAN_E_UNSUPPORTED;
+  }
+  if (getenv("GSCAN_DEBUG")) fprintf(stderr, "[gscan] v3 bwd sweep: smem %zu B, max co-resident clusters %d\n", bytes, max_clusters);
+  ok = true;
+  return 0;
+}
+
+bool v3_bwd_shape_ok(const gscan_dims& d) {
+  static const bool off = getenv("GSCAN_BWD_V1") != nullptr;
+  if (off || !v3_shape_ok(d) || d.Ti > v3::kMaxTiB) return false;
+  const size_t bytes = (size_t)v3::bwd_smem(d.Ti, d.conditional_attention ? 1 : 0).total * sizeof(float);
+  return bytes <= kMaxSmemBytes;
+}
+
+int launch_dec_bwd_v3(const gscan_dims& d, v3::DecBwd3P p, cudaStream_t st) {
+  const int cond = d.conditional_attention ? 1 : 0;
+  const size_t bytes = (size_t)v3::bwd_smem(d.Ti, cond).total * sizeof(float);
+  TRY(cond ? v3_bwd_prepare<true>(bytes) : v3_bwd_prepare<false>(bytes));
+  static const bool want_timeline = getenv("GSCAN_TIMELINE") != nullptr;
+  long long* tl = nullptr;
+  if (want_timeline) {
+    cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
+    p.timeline = tl;
+  }
+  const int grid = ceil_div(d.B, v3::kNB) * v3::kC;
+  if (cond) v3::dec_bwd_v3_kernel<true><<<grid, v3::kThreads, bytes, st>>>(p);
+  else v3::dec_bwd_v3_kernel<false><<<grid, v3::kThreads, bytes, st>>>(p);
+  GSCAN_CHECK_LAUNCH();
+  if (tl) print_timeline("v3 bwd", tl, p.T, st);
+  return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -796,7 +856,35 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   bp.dKT = ws + L.dKT; bp.dKV = ws + L.dKV; bp.dh0 = ws + L.dh0;
   bp.dvT = ws + L.dvec; bp.dvV = ws + L.dvec + H;
   prof_mark(6, st);
-  TRY(launch_dec_bwd(*d, bp, st));
+  bool bwd_v3 = false;
+  if (v3_bwd_shape_ok(*d)) {
+    v3::DecBwd3P b3{};
+    b3.B = B; b3.T = Tt; b3.Ti = Ti;
+    b3.W_ih = bp.W_ih; b3.W_hh = bp.W_hh; b3.W_qV = bp.W_qV; b3.W_c = bp.W_c; b3.W_qT = bp.W_qT;
+    b3.PT = ws + L.PT;   // computed by the forward call on this workspace
+    b3.vT = bp.vT; b3.vV = bp.vV; b3.KT = bp.KT; b3.KV = bp.KV; b3.cmd_len = cmd_len;
+    b3.Cs = bp.Cs; b3.gates = bp.gates; b3.alpha = bp.alpha; b3.beta = bp.beta; b3.Qp = bp.Qp; b3.qT = bp.qT; b3.qV = bp.qV;
+    b3.dU = bp.dU; b3.dbeta_aux = dbeta_aux;
+    b3.dgates = bp.dgates; b3.dd = bp.dd; b3.dqV = bp.dqV; b3.dqT = bp.dqT;
+    b3.dKT = bp.dKT; b3.dKV = bp.dKV; b3.dh0 = bp.dh0; b3.dvT = bp.dvT; b3.dvV = bp.dvV;
+    int rc = launch_dec_bwd_v3(*d, b3, st);
+    if (rc == 0) bwd_v3 = true;
+    else if (rc != GSCAN_E_UNSUPPORTED) return rc;
+  }
+  if (bwd_v3) {
+    // value path of both attentions, outside the recurrence: dc_T, dc_V for all steps as batched products,
+    // accumulated into the (already consumed) [c_T | c_V] columns of dU, then dK += sum_t w_t dc_t
+    TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH] + H, 3 * H, ws + L.dU + 2 * H, 4 * H, R, 2 * H, 4 * H, 1, st));
+    if (d->conditional_attention)
+      TRY(matmul_nn(ws + L.dd, H, P[GSCAN_P_COND_W] + H, 2 * H, ws + L.dU + 2 * H, 4 * H, R, H, H, 1, st));
+    size_t smem = sizeof(float) * (size_t)Tt * (M > Ti ? M : Ti);
+    if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_bwd_kernel, smem));
+    v3::attn_value_bwd_kernel<<<dim3(B, 2), 256, smem, st>>>(ws + L.dU + 2 * H, 4 * H, ws + L.beta, ws + L.alpha, B, Tt, Ti,
+                                                             M, H, ws + L.dKV, ws + L.dKT);
+    GSCAN_CHECK_LAUNCH();
+  } else {
+    TRY(launch_dec_bwd(*d, bp, st));
+  }
   prof_mark(7, st);
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
