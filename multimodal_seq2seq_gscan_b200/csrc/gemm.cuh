@@ -1,4 +1,4 @@
-// Generic fp32 GEMM on the FMA pipe (FFMA2), used for every batched (off-the-recurrence)
+// Generic fp32-accurate GEMM on the tensor cores, used for every batched (off-the-recurrence)
 // contraction of the path: key projections, input-gate pre-activations of all steps at once,
 // the output projection, and all weight gradients (as split-K "TN" products).
 //
@@ -7,6 +7,13 @@
 //
 // so NT / NN / TN forms are all the same kernel with different strides; the tile loaders pick the
 // lane mapping that makes the contiguous axis the coalesced one.
+//
+// Arithmetic: mma.sync.m16n8k8 tf32 in split precision (3xTF32): every fp32 operand x is used as
+// x_hi = top 19 bits (what the tensor core reads) and x_lo = x - x_hi, and A.B is accumulated in fp32
+// as A_hi B_hi + A_lo B_hi + A_hi B_lo.  The dropped A_lo B_lo term is ~2^-21 relative, which keeps
+// the 1e-4 parity bar against the fp32 reference with two orders of magnitude to spare.
+// (The operands are fp32 activations / gradients produced on the fly, so a tcgen05 + TMA pipeline
+// would need a separate hi/lo staging pass per operand tile)
 #pragma once
 #include "common.cuh"
 
@@ -23,116 +30,258 @@ struct GemmP {
   int kchunk;      // K range per blockIdx.z (multiple of BK); gridDim.z > 1 => atomicAdd epilogue
 };
 
-constexpr int GBM = 128, GBN = 64, GBK = 16, GTHREADS = 256;
+constexpr int GBM = 128, GBN = 64, GBK = 32, GTHREADS = 256, GSTAGES = 3;
+constexpr int GLDK = GBK + 4;    // row stride of a k-contiguous operand tile  [rows][GLDK]
+constexpr int GLDAM = GBM + 8;   // row stride of an m-contiguous A tile       [GBK][GLDAM]
+constexpr int GLDBN = GBN + 8;   // row stride of an n-contiguous B tile       [GBK][GLDBN]
+// (GLDK % 32 == 4, GLDAM % 32 == 8, GLDBN % 32 == 8: every fragment load below is bank-conflict free)
 
-__global__ void __launch_bounds__(GTHREADS) sgemm_kernel(GemmP p) {
-  __shared__ __align__(16) float As[GBK][GBM + 4];
-  __shared__ __align__(16) float Bs[GBK][GBN + 4];
+__device__ __forceinline__ void gemm_mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// round-to-nearest tf32 part of x; the remainder x - hi is the low part (|lo| <= 2^-12 |x|, either sign,
+// so the dropped lo*lo terms stay ~2^-24 relative and do not accumulate a bias over a long K)
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, int bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, int bytes) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__host__ __device__ constexpr int gemm_a_stage(bool ak) { return ak ? GBM * GLDK : GBK * GLDAM; }
+__host__ __device__ constexpr int gemm_b_stage(bool bk) { return bk ? GBN * GLDK : GBK * GLDBN; }
+
+// AK / BKF: the operand is contiguous along k in global memory (else along m / n).
+// VEC: 16-byte copies are legal (base pointers and leading dimensions 16-byte aligned).
+template <bool AK, bool BKF, bool VEC>
+__global__ void __launch_bounds__(GTHREADS, 2) sgemm_kernel(GemmP p) {
+  extern __shared__ __align__(16) float gsm[];
+  constexpr int ASZ = gemm_a_stage(AK), BSZ = gemm_b_stage(BKF);
+  float* As = gsm;
+  float* Bs = gsm + GSTAGES * ASZ;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1;   // 4 x 2 warps, 32 x 32 outputs each
+  const int fg = lane >> 2, ft = lane & 3;
   const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
   const int k_begin = blockIdx.z * p.kchunk;
   const int k_end = min(p.K, k_begin + p.kchunk);
-  const bool a_kfast = (p.a_cs == 1);
-  const bool b_kfast = (p.b_rs == 1);
+  const int nk = k_end > k_begin ? (k_end - k_begin + GBK - 1) / GBK : 0;
+  const long lda = AK ? p.a_rs : p.a_cs, ldb = BKF ? p.b_cs : p.b_rs;
 
-  float a_reg[8], b_reg[4];
-  auto load_tiles = [&](int kt) {
+  auto issue = [&](int stage, int kt) {
+    float* as = As + stage * ASZ;
+    float* bs = Bs + stage * BSZ;
+    if (AK) {   // [GBM rows][GBK k]
+      if (VEC) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int e = tid + i * GTHREADS;
-      int kk = a_kfast ? (e & (GBK - 1)) : (e / GBM);
-      int mm = a_kfast ? (e / GBK) : (e % GBM);
-      int gm = m0 + mm, gk = kt + kk;
-      a_reg[i] = (gm < p.M && gk < k_end) ? __ldg(p.A + (long)gm * p.a_rs + (long)gk * p.a_cs) : 0.f;
-    }
+        for (int i = 0; i < GBM * GBK / 4 / GTHREADS; ++i) {
+          const int c = tid + i * GTHREADS, r = c / (GBK / 4), kq = c % (GBK / 4);
+          const int gm = m0 + r, gk = kt + 4 * kq;
+          const int bytes = gm < p.M ? max(0, min(16, (k_end - gk) * 4)) : 0;
+          cp_async16(as + r * GLDK + 4 * kq, bytes ? p.A + (long)gm * lda + gk : p.A, bytes);
+        }
+      } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int e = tid + i * GTHREADS;
-      int kk = b_kfast ? (e & (GBK - 1)) : (e / GBN);
-      int nn = b_kfast ? (e / GBK) : (e % GBN);
-      int gn = n0 + nn, gk = kt + kk;
-      b_reg[i] = (gn < p.N && gk < k_end) ? __ldg(p.B + (long)gk * p.b_rs + (long)gn * p.b_cs) : 0.f;
-    }
-  };
-  auto store_tiles = [&]() {
+        for (int i = 0; i < GBM * GBK / GTHREADS; ++i) {
+          const int e = tid + i * GTHREADS, r = e / GBK, k = e % GBK;
+          const int gm = m0 + r, gk = kt + k;
+          const int bytes = (gm < p.M && gk < k_end) ? 4 : 0;
+          cp_async4(as + r * GLDK + k, bytes ? p.A + (long)gm * lda + gk : p.A, bytes);
+        }
+      }
+    } else {    // [GBK k][GBM m]
+      if (VEC) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int e = tid + i * GTHREADS;
-      int kk = a_kfast ? (e & (GBK - 1)) : (e / GBM);
-      int mm = a_kfast ? (e / GBK) : (e % GBM);
-      As[kk][mm] = a_reg[i];
-    }
+        for (int i = 0; i < GBM * GBK / 4 / GTHREADS; ++i) {
+          const int c = tid + i * GTHREADS, k = c / (GBM / 4), mq = c % (GBM / 4);
+          const int gm = m0 + 4 * mq, gk = kt + k;
+          const int bytes = gk < k_end ? max(0, min(16, (p.M - gm) * 4)) : 0;
+          cp_async16(as + k * GLDAM + 4 * mq, bytes ? p.A + (long)gk * lda + gm : p.A, bytes);
+        }
+      } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int e = tid + i * GTHREADS;
-      int kk = b_kfast ? (e & (GBK - 1)) : (e / GBN);
-      int nn = b_kfast ? (e / GBK) : (e % GBN);
-      Bs[kk][nn] = b_reg[i];
-    }
-  };
-
-  float2 acc[8][2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
-
-  if (k_begin < k_end) {
-    load_tiles(k_begin);
-    store_tiles();
-  }
-  __syncthreads();
-  for (int kt = k_begin; kt < k_end; kt += GBK) {
-    const bool more = (kt + GBK < k_end);
-    if (more) load_tiles(kt + GBK);
-#pragma unroll
-    for (int kk = 0; kk < GBK; ++kk) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
-      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-      float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
-      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float2 aa = make_float2(av[i], av[i]);
-        fma2(acc[i][0], aa, b01);
-        fma2(acc[i][1], aa, b23);
+        for (int i = 0; i < GBM * GBK / GTHREADS; ++i) {
+          const int e = tid + i * GTHREADS, k = e / GBM, m = e % GBM;
+          const int gm = m0 + m, gk = kt + k;
+          const int bytes = (gm < p.M && gk < k_end) ? 4 : 0;
+          cp_async4(as + k * GLDAM + m, bytes ? p.A + (long)gk * lda + gm : p.A, bytes);
+        }
       }
     }
-    __syncthreads();
-    if (more) {
-      store_tiles();
-      __syncthreads();
+    if (BKF) {  // [GBN rows][GBK k]
+      if (VEC) {
+#pragma unroll
+        for (int i = 0; i < GBN * GBK / 4 / GTHREADS; ++i) {
+          const int c = tid + i * GTHREADS, r = c / (GBK / 4), kq = c % (GBK / 4);
+          const int gn = n0 + r, gk = kt + 4 * kq;
+          const int bytes = gn < p.N ? max(0, min(16, (k_end - gk) * 4)) : 0;
+          cp_async16(bs + r * GLDK + 4 * kq, bytes ? p.B + (long)gn * ldb + gk : p.B, bytes);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < GBN * GBK / GTHREADS; ++i) {
+          const int e = tid + i * GTHREADS, r = e / GBK, k = e % GBK;
+          const int gn = n0 + r, gk = kt + k;
+          const int bytes = (gn < p.N && gk < k_end) ? 4 : 0;
+          cp_async4(bs + r * GLDK + k, bytes ? p.B + (long)gn * ldb + gk : p.B, bytes);
+        }
+      }
+    } else {    // [GBK k][GBN n]
+      if (VEC) {
+#pragma unroll
+        for (int i = 0; i < GBN * GBK / 4 / GTHREADS; ++i) {
+          const int c = tid + i * GTHREADS, k = c / (GBN / 4), nq = c % (GBN / 4);
+          const int gn = n0 + 4 * nq, gk = kt + k;
+          const int bytes = gk < k_end ? max(0, min(16, (p.N - gn) * 4)) : 0;
+          cp_async16(bs + k * GLDBN + 4 * nq, bytes ? p.B + (long)gk * ldb + gn : p.B, bytes);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < GBN * GBK / GTHREADS; ++i) {
+          const int e = tid + i * GTHREADS, k = e / GBN, n = e % GBN;
+          const int gn = n0 + n, gk = kt + k;
+          const int bytes = (gn < p.N && gk < k_end) ? 4 : 0;
+          cp_async4(bs + k * GLDBN + n, bytes ? p.B + (long)gk * ldb + gn : p.B, bytes);
+        }
+      }
     }
+  };
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+#pragma unroll
+  for (int s = 0; s < GSTAGES - 1; ++s) {
+    if (s < nk) issue(s, k_begin + s * GBK);
+    cp_async_commit();
   }
+  for (int it = 0; it < nk; ++it) {
+    cp_async_wait<GSTAGES - 2>();
+    __syncthreads();   // tile `it` has landed for everyone; the stage refilled below was consumed in iteration it-1
+    if (it + GSTAGES - 1 < nk) issue((it + GSTAGES - 1) % GSTAGES, k_begin + (it + GSTAGES - 1) * GBK);
+    cp_async_commit();
+    const float* as = As + (it % GSTAGES) * ASZ;
+    const float* bs = Bs + (it % GSTAGES) * BSZ;
+    // The tensor core adds into its fp32 accumulator with truncation, which over a K of thousands grows into a
+    // bias of ~K/8 half-ulps of the running sum.  So each 32-deep tile is accumulated from zero on the tensor
+    // core and folded into the running sum with a round-to-nearest fp32 add.
+    float tmp[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmp[i][j][c] = 0.f;
+#pragma unroll
+    for (int k8 = 0; k8 < GBK; k8 += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int mrow = wm * 32 + mt * 16 + fg;
+        float v[4];
+        if (AK) {
+          v[0] = as[mrow * GLDK + k8 + ft]; v[1] = as[(mrow + 8) * GLDK + k8 + ft];
+          v[2] = as[mrow * GLDK + k8 + ft + 4]; v[3] = as[(mrow + 8) * GLDK + k8 + ft + 4];
+        } else {
+          v[0] = as[(k8 + ft) * GLDAM + mrow]; v[1] = as[(k8 + ft) * GLDAM + mrow + 8];
+          v[2] = as[(k8 + ft + 4) * GLDAM + mrow]; v[3] = as[(k8 + ft + 4) * GLDAM + mrow + 8];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ah[mt][c] = tf32_rna(v[c]);
+          al[mt][c] = __float_as_uint(v[c] - __uint_as_float(ah[mt][c]));
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int ncol = wn * 32 + nt * 8 + fg;
+        float v[2];
+        if (BKF) { v[0] = bs[ncol * GLDK + k8 + ft]; v[1] = bs[ncol * GLDK + k8 + ft + 4]; }
+        else { v[0] = bs[(k8 + ft) * GLDBN + ncol]; v[1] = bs[(k8 + ft + 4) * GLDBN + ncol]; }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          bh[nt][c] = tf32_rna(v[c]);
+          bl[nt][c] = __float_as_uint(v[c] - __uint_as_float(bh[nt][c]));
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          gemm_mma_tf32(tmp[mt][nt], al[mt], bh[nt]);
+          gemm_mma_tf32(tmp[mt][nt], ah[mt], bl[nt]);
+          gemm_mma_tf32(tmp[mt][nt], ah[mt], bh[nt]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][j][c] += tmp[i][j][c];
+  }
+  cp_async_wait<0>();
 
   const bool split = gridDim.z > 1;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    if (gm >= p.M) continue;
-    float v[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+  for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int gn = n0 + tx * 4 + j;
-      if (gn >= p.N) continue;
-      float* c = p.C + (long)gm * p.ldc + gn;
-      if (split) {
-        atomicAdd(c, v[j]);
-      } else {
-        float r = v[j];
-        if (p.bias) r += __ldg(p.bias + gn);
-        if (p.bias2) r += __ldg(p.bias2 + gn);
-        if (p.act == 1) r = act_tanh(r);
-        else if (p.act == 2) r = fmaxf(r, 0.f);
-        if (p.accumulate) r += *c;
-        *c = r;
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int gm = m0 + wm * 32 + mt * 16 + fg + 8 * (c >> 1);
+        const int gn = n0 + wn * 32 + nt * 8 + 2 * ft + (c & 1);
+        if (gm >= p.M || gn >= p.N) continue;
+        float* cp = p.C + (long)gm * p.ldc + gn;
+        if (split) {
+          atomicAdd(cp, acc[mt][nt][c]);
+        } else {
+          float r = acc[mt][nt][c];
+          if (p.bias) r += __ldg(p.bias + gn);
+          if (p.bias2) r += __ldg(p.bias2 + gn);
+          if (p.act == 1) r = act_tanh(r);
+          else if (p.act == 2) r = fmaxf(r, 0.f);
+          if (p.accumulate) r += *cp;
+          *cp = r;
+        }
       }
-    }
+}
+
+template <bool AK, bool BKF, bool VEC>
+inline int launch_sgemm_t(const GemmP& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t bytes = sizeof(float) * GSTAGES * (gemm_a_stage(AK) + gemm_b_stage(BKF));
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(sgemm_kernel<AK, BKF, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
   }
+  sgemm_kernel<AK, BKF, VEC><<<grid, GTHREADS, bytes, st>>>(p);
+  GSCAN_CHECK_LAUNCH();
+  return 0;
 }
 
 // Launch helper.  ksplit > 1 requires C to be initialised (zero, or the value to accumulate
-// onto) and forbids bias / act.
+// onto) and forbids bias / act.  Each operand must be contiguous along one of its two axes.
 inline int launch_sgemm(const float* A, long a_rs, long a_cs, const float* B, long b_rs, long b_cs,
                         float* C, long ldc, int M, int N, int K, const float* bias, const float* bias2,
                         int act, int accumulate, int ksplit, cudaStream_t st) {
@@ -144,9 +293,15 @@ inline int launch_sgemm(const float* A, long a_rs, long a_cs, const float* B, lo
   ksplit = K > 0 ? ceil_div(K, kchunk) : 1;
   p.kchunk = (ksplit == 1) ? max(K, 1) : kchunk;
   dim3 grid(ceil_div(N, GBN), ceil_div(M, GBM), ksplit);
-  sgemm_kernel<<<grid, GTHREADS, 0, st>>>(p);
-  GSCAN_CHECK_LAUNCH();
-  return 0;
+  const bool ak = (a_cs == 1), bk = (b_rs == 1);
+  if ((!ak && a_rs != 1) || (!bk && b_cs != 1)) return -2;   // GSCAN_E_UNSUPPORTED: no unit stride
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const long lda = ak ? a_rs : a_cs, ldb = bk ? b_cs : b_rs;
+  const bool vec = al16(A) && al16(B) && (lda % 4 == 0) && (ldb % 4 == 0);
+  if (ak && bk) return vec ? launch_sgemm_t<true, true, true>(p, grid, st) : launch_sgemm_t<true, true, false>(p, grid, st);
+  if (ak && !bk) return vec ? launch_sgemm_t<true, false, true>(p, grid, st) : launch_sgemm_t<true, false, false>(p, grid, st);
+  if (!ak && !bk) return vec ? launch_sgemm_t<false, false, true>(p, grid, st) : launch_sgemm_t<false, false, false>(p, grid, st);
+  return vec ? launch_sgemm_t<false, true, true>(p, grid, st) : launch_sgemm_t<false, true, false>(p, grid, st);
 }
 
 // Weight-gradient form: C[N1,N2] (ldc) = sum_r X[r, i] * Y[r, j] over R rows (R large).
