@@ -46,6 +46,34 @@ __device__ __forceinline__ float act_sigmoid(float x) {
 }
 #endif
 
+// N tanh evaluations sharing ONE reciprocal: tanh(x_i) = 1 - 2 / d_i with d_i = 1 + e^{2 x_i}, and
+// 1/d_i = (prod_{j != i} d_j) / (prod_j d_j).  N ex2 + 1 rcp on the SFU instead of 2N, the products go to the
+// FMA pipe.  The clamp keeps prod_j d_j finite for N <= 5 (d <= e^17.2) and costs nothing: tanh(8.6) rounds to 1.
+#ifdef GSCAN_PRECISE_MATH
+template <int N>
+__device__ __forceinline__ void act_tanh_n(const float (&x)[N], float (&y)[N]) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = tanhf(x[i]);
+}
+#else
+template <int N>
+__device__ __forceinline__ void act_tanh_n(const float (&x)[N], float (&y)[N]) {
+  static_assert(N >= 2 && N <= 5, "product of N denominators must stay below FLT_MAX");
+  float d[N], pre[N], suf[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) d[i] = 1.0f + __expf(2.0f * fminf(fmaxf(x[i], -8.6f), 8.6f));
+  pre[0] = 1.0f;
+#pragma unroll
+  for (int i = 1; i < N; ++i) pre[i] = pre[i - 1] * d[i - 1];      // prod_{j < i} d_j
+  suf[N - 1] = 1.0f;
+#pragma unroll
+  for (int i = N - 2; i >= 0; --i) suf[i] = suf[i + 1] * d[i + 1];  // prod_{j > i} d_j
+  const float r = __fdividef(2.0f, pre[N - 1] * d[N - 1]);          // 2 / prod_j d_j
+#pragma unroll
+  for (int i = 0; i < N; ++i) y[i] = fmaf(-r, pre[i] * suf[i], 1.0f);
+}
+#endif
+
 // Packed fp32 FMA (FFMA2, new on sm_100): two independent IEEE fp32 FMAs per issue slot.
 __device__ __forceinline__ void fma2(float2& acc, const float2 a, const float2 b) {
   acc = __ffma2_rn(a, b, acc);

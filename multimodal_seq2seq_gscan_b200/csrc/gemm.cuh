@@ -42,13 +42,10 @@ __device__ __forceinline__ void gemm_mma_tf32(float (&d)[4], const uint32_t (&a)
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// round-to-nearest tf32 part of x; the remainder x - hi is the low part (|lo| <= 2^-12 |x|, either sign,
+// round-to-nearest tf32 part of x (integer add + mask; cvt.rna.tf32.f32 is several times slower to issue);
+// the remainder x - hi is the low part (|lo| <= 2^-12 |x|, either sign,
 // so the dropped lo*lo terms stay ~2^-24 relative and do not accumulate a bias over a long K)
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+__device__ __forceinline__ uint32_t tf32_rna(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void cp_async16(float* dst, const float* src, int bytes) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
@@ -312,7 +309,7 @@ inline int launch_grad_gemm(const float* X, long ldx, const float* Y, long ldy, 
   cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, N2 * sizeof(float), N1, st);
   if (e != cudaSuccess) return (int)e;
   int tiles = ceil_div(N1, GBM) * ceil_div(N2, GBN);
-  int ksplit = max(1, min(ceil_div(R, 4 * GBK), ceil_div(2 * num_sms, tiles)));
+  int ksplit = max(1, min(ceil_div(R, 4 * GBK), (2 * num_sms) / tiles));   // one wave at 2 CTAs per SM
   return launch_sgemm(X, 1, ldx, Y, ldy, 1, C, ldc, N1, N2, R, nullptr, nullptr, 0, 0, ksplit, st);
 }
 
