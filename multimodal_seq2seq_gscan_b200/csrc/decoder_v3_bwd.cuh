@@ -588,22 +588,45 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
 __global__ void __launch_bounds__(256) attn_value_bwd_kernel(const float* __restrict__ dc, long ldc, const float* __restrict__ beta,
                                                              const float* __restrict__ alpha, int B, int T, int Ti, int M, int H,
                                                              float* __restrict__ dKV, float* __restrict__ dKT) {
-  extern __shared__ float w_s[];   // [T][N] attention weights of this example
+  // per example a [N x T] . [T x H] product with both operands staged in shared memory:
+  // w_s [T][NP] attention weights (NP = N rounded up to 4), dc_s [T][H] context gradients
+  extern __shared__ __align__(16) float av_s[];
   const int b = blockIdx.x, vis = blockIdx.y == 0;
-  const int N = vis ? M : Ti;
+  const int N = vis ? M : Ti, NP = (N + 3) & ~3;
   const float* w = vis ? beta : alpha;
-  for (int i = threadIdx.x; i < T * N; i += blockDim.x) {
-    const int t = i / N, k = i - t * N;
-    w_s[i] = __ldg(w + ((size_t)t * B + b) * N + k);
+  float* w_s = av_s;
+  float* dc_s = av_s + (size_t)T * NP;
+  for (int i = threadIdx.x; i < T * NP; i += blockDim.x) {
+    const int t = i / NP, k = i - t * NP;
+    w_s[i] = k < N ? __ldg(w + ((size_t)t * B + b) * N + k) : 0.f;
+  }
+  const float* dcb = dc + (vis ? H : 0);
+  for (int i = threadIdx.x; i < T * H; i += blockDim.x) {
+    const int t = i / H, h = i - t * H;
+    dc_s[i] = __ldg(dcb + ((size_t)t * B + b) * ldc + h);
   }
   __syncthreads();
-  const float* dcb = dc + (vis ? H : 0);
-  for (int o = threadIdx.x; o < N * H; o += blockDim.x) {
-    const int k = o / H, h = o - k * H;
-    float acc = 0.f;
-    for (int t = 0; t < T; ++t) acc = fmaf(w_s[t * N + k], __ldg(dcb + ((size_t)t * B + b) * ldc + h), acc);
-    if (vis) dKV[((size_t)b * M + k) * H + h] += acc;
-    else dKT[((size_t)k * B + b) * H + h] += acc;
+  // thread = (hidden h, key quad group): 4 keys x 1 hidden per accumulator set, keys strided by the group count
+  const int HP = (H + 31) & ~31;                 // lanes per key group, warp aligned
+  const int groups = blockDim.x / HP;            // 2 for H = 100
+  const int grp = threadIdx.x / HP, h = threadIdx.x - grp * HP;
+  if (grp >= groups || h >= H) return;
+  for (int k0 = 4 * grp; k0 < NP; k0 += 4 * groups) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const float4 wv = *reinterpret_cast<const float4*>(w_s + t * NP + k0);
+      const float d = dc_s[t * H + h];
+      acc.x = fmaf(wv.x, d, acc.x); acc.y = fmaf(wv.y, d, acc.y); acc.z = fmaf(wv.z, d, acc.z); acc.w = fmaf(wv.w, d, acc.w);
+    }
+    const float a[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = k0 + u;
+      if (k < N) {
+        if (vis) dKV[((size_t)b * M + k) * H + h] += a[u];
+        else dKT[((size_t)k * B + b) * H + h] += a[u];
+      }
+    }
   }
 }
 

@@ -877,7 +877,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH] + H, 3 * H, ws + L.dU + 2 * H, 4 * H, R, 2 * H, 4 * H, 1, st));
     if (d->conditional_attention)
       TRY(matmul_nn(ws + L.dd, H, P[GSCAN_P_COND_W] + H, 2 * H, ws + L.dU + 2 * H, 4 * H, R, H, H, 1, st));
-    size_t smem = sizeof(float) * (size_t)Tt * (M > Ti ? M : Ti);
+    size_t smem = sizeof(float) * (size_t)Tt * ((((M > Ti ? M : Ti) + 3) & ~3) + H);
     if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_bwd_kernel, smem));
     v3::attn_value_bwd_kernel<<<dim3(B, 2), 256, smem, st>>>(ws + L.dU + 2 * H, 4 * H, ws + L.beta, ws + L.alpha, B, Tt, Ti,
                                                              M, H, ws + L.dKV, ws + L.dKT);
@@ -907,7 +907,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   {
     TRYCUDA(cudaMemsetAsync(G[GSCAN_P_DEC_EMB], 0, sizeof(float) * (size_t)V * H, st));
     int use_smem = ((size_t)V * H * sizeof(float) <= 48 * 1024);
-    int rpb = 128;
+    int rpb = 64;
     embed_bwd_kernel<<<ceil_div(R, rpb), 256, use_smem ? (size_t)V * H * sizeof(float) : 0, st>>>(
         tgts, Tt, ws + L.dU, 4 * H, drop_dec, G[GSCAN_P_DEC_EMB], H, V, d->pad_idx_out, B, Tt, 1, rpb, use_smem);
     GSCAN_CHECK_LAUNCH();

@@ -69,19 +69,21 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
   const long R = (long)B * T;
   long r0 = (long)blockIdx.x * rows_per_block;
   long r1 = min(R, r0 + rows_per_block);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   if (use_smem) {
     for (int i = threadIdx.x; i < Vsz * Wd; i += blockDim.x) acc_s[i] = 0.f;
     __syncthreads();
   }
-  for (long r = r0; r < r1; ++r) {
+  // one warp per row: the rows of a block are in flight together instead of one after the other
+  for (long r = r0 + warp; r < r1; r += nwarps) {
     int b = r / T, t = r - (long)b * T;
     long long tok = tokens[(long)b * tok_stride + t];
     if (tok == pad) continue;
     long xrow = row_mode == 0 ? r : ((long)t * B + b);
-    for (int h = threadIdx.x; h < Wd; h += blockDim.x) {
+    for (int h = lane; h < Wd; h += 32) {
       float g = __ldg(dX + xrow * ldx + h);
       if (mask) g *= __ldg(mask + r * Wd + h);
-      if (use_smem) acc_s[tok * Wd + h] += g;   // distinct h per thread: no race
+      if (use_smem) atomicAdd(acc_s + tok * Wd + h, g);
       else atomicAdd(dW + tok * Wd + h, g);
     }
   }
@@ -200,11 +202,21 @@ __global__ void __launch_bounds__(1024) nll_forward_kernel(const float* __restri
   __shared__ float s_cnt[32];
   float sum = 0.f, cnt = 0.f;
   const long R = (long)B * T;
-  for (long r = threadIdx.x; r < R; r += blockDim.x) {
-    int b = r / T, t = r - (long)b * T;
-    if (t + shift < T) {
-      long long y = tgt[(long)b * T + t + shift];
-      if (y != pad) { sum -= __ldg(logp + r * V + y); cnt += 1.f; }
+  for (long rb = threadIdx.x; rb < R; rb += 4L * blockDim.x) {
+    long long y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {   // all targets first, then all log-probs: 4 dependent pairs in flight
+      const long r = rb + (long)u * blockDim.x;
+      y[u] = pad;
+      if (r < R) {
+        int b = r / T, t = r - (long)b * T;
+        if (t + shift < T) y[u] = tgt[(long)b * T + t + shift];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long r = rb + (long)u * blockDim.x;
+      if (y[u] != pad) { sum -= __ldg(logp + r * V + y[u]); cnt += 1.f; }
     }
   }
   sum = warp_sum(sum); cnt = warp_sum(cnt);
