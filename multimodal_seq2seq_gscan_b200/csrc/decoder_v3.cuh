@@ -123,8 +123,9 @@ __device__ __forceinline__ void mv_tile(const uint32_t (&whi)[kKSteps][4], const
 // ---- shared-memory layout (float offsets) --------------------------------------------------------
 struct FwdSmem {
   int hfull, qpfull, cvfull, xT, xV, P, KT, KV, qT, ch, qV, g, al, be, vT, vV, bc, len, bars, wlo, total;
+  int xeTab, outE, wo, u, xL, tok;   // greedy decoding only
 };
-__host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond) {
+__host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond, int greedy_V = 0) {
   FwdSmem s{};
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
@@ -149,6 +150,15 @@ __host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond) {
   s.len = take(kNB);
   s.bars = take(16);   // 5 mbarriers (8 bytes each)
   s.wlo = take(15 * kKSteps * 32 * 4);   // W_lo fragments: [role warp][k-step][lane] float4
+  if (greedy_V > 0) {
+    const int V = greedy_V, Vp = (V + 3) & ~3;
+    s.xeTab = take(V * kG4);       // this CTA's columns of Emb . W_ih[:, :H]^T + b_ih + b_hh
+    s.outE = take(V * V);          // OutE[tok][v] = Wout[v, :H] . Emb[tok]
+    s.wo = take(3 * kHS * Vp);     // rows of Wout[:, H:4H]^T for this CTA's slices of h, c_T, c_V
+    s.u = take(kNB * 3 * kHS);     // [h | c_T | c_V] slices of the current step
+    s.xL = take(kC * kNB * Vp);    // partial logits from every rank
+    s.tok = take(3 * kNB + 4);     // tok, alive, flag (ints)
+  }
   s.total = o;
   return s;
 }
@@ -165,6 +175,12 @@ struct DecFwd3P {
   const float* Xe;                // [T][B][4H]
   float *U, *Cs, *gates, *alpha, *beta, *Qp, *qT, *qV, *beta_sum;   // saved activations (recurrent.cuh DecFwdP)
   long long* timeline;   // debug: [T][16] clock64 stamps of CTA 0, else null
+  // greedy decoding (predict.py:97-117); tables as in recurrent.cuh DecFwdP
+  const float *XeTab, *OutE, *Wo_t;
+  int V, Vp, sos, eos;
+  long long* out_tokens;   // [B][T]
+  int *out_len, *out_steps;
+  float *g_alphas, *g_betas;   // [B][T][Ti], [B][T][M] or null
 };
 
 #define GSCAN3_STAMP(k)                                                                            \
@@ -282,7 +298,7 @@ __device__ __forceinline__ void partial_scores(const float* __restrict__ q_s, co
   }
 }
 
-template <bool COND>
+template <bool COND, bool GREEDY>
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fwd_v3_kernel(DecFwd3P p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RBl = kHS * (4 + (COND ? 1 : 0));
@@ -294,7 +310,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   const int b0 = (blockIdx.x / kC) * kNB;
   const int nb = min(kNB, B - b0);
   const int S0 = rank * kHS;
-  const FwdSmem L = fwd_smem(Ti, COND ? 1 : 0);
+  const FwdSmem L = fwd_smem(Ti, COND ? 1 : 0, GREEDY ? p.V : 0);
 
   float* hfull_s = smem + L.hfull;
   float* qpfull_s = smem + L.qpfull;
@@ -314,9 +330,17 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   float* vV_s = smem + L.vV;
   float* bc_s = smem + L.bc;
   int* len_s = reinterpret_cast<int*>(smem + L.len);
+  float* xeTab_s = smem + L.xeTab;
+  float* outE_s = smem + L.outE;
+  float* wo_s = smem + L.wo;
+  float* u_s = smem + L.u;
+  float* xL_s = smem + L.xL;
+  int* tok_s = reinterpret_cast<int*>(smem + L.tok);
+  int* alive_s = tok_s + kNB;
+  int* flag_s = alive_s + kNB;
 
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar0 = smem_base + (uint32_t)L.bars * 4u;   // [0] xT  [1] qp  [2] xV  [3] cv  [4] h
+  const uint32_t bar0 = smem_base + (uint32_t)L.bars * 4u;   // [0] xT  [1] qp  [2] xV  [3] cv  [4] h  [5] logits
   uint32_t rb[kC];
 #pragma unroll
   for (int d = 0; d < kC; ++d) rb[d] = mapa_u32(smem_base, (uint32_t)d);
@@ -399,7 +423,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       hfull_s[i] = hv;
       qpfull_s[i] = 0.f;
       cvfull_s[i] = 0.f;
-      if (n < nb && h >= S0 && h < S0 + kHS) p.U[(size_t)(b0 + n) * H4 + kH + h] = hv;   // row group 0: h_{-1}
+      if (!GREEDY && n < nb && h >= S0 && h < S0 + kHS) p.U[(size_t)(b0 + n) * H4 + kH + h] = hv;   // row group 0: h_{-1}
     }
     for (int i = tid; i < kNB * kGS; i += kThreads) g_s[i] = 0.f;
     if (tid < kHS) {
@@ -408,8 +432,24 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       bc_s[tid] = COND ? __ldg(p.bc + S0 + tid) : 0.f;
     }
     if (tid < kNB) len_s[tid] = (tid < nb) ? max(1, min(p.cmd_len[b0 + tid], Ti)) : 1;
+    if (GREEDY) {
+      const int V = p.V, Vp = p.Vp;
+      for (int i = tid; i < V * kG4; i += kThreads) {
+        const int v = i / kG4, c = i - v * kG4;
+        xeTab_s[i] = __ldg(p.XeTab + (size_t)v * H4 + (c / kHS) * kH + S0 + (c % kHS));
+      }
+      for (int i = tid; i < V * V; i += kThreads) outE_s[i] = __ldg(p.OutE + i);
+      for (int i = tid; i < 3 * kHS * Vp; i += kThreads) {
+        const int k = i / Vp, v = i - k * Vp;   // k = part * 20 + hidden offset
+        wo_s[i] = __ldg(p.Wo_t + (size_t)((k / kHS) * kH + S0 + (k % kHS)) * Vp + v);
+      }
+      if (tid < kNB) {
+        tok_s[tid] = p.sos;
+        alive_s[tid] = tid < nb ? 1 : 0;
+      }
+    }
     if (tid == 0) {
-      for (int k = 0; k < 5; ++k) mbar_init(bar0 + 8u * k, 1);
+      for (int k = 0; k < 6; ++k) mbar_init(bar0 + 8u * k, 1);
       fence_mbar_init();
     }
   }
@@ -419,9 +459,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   if (tid < kNB * kHS) {
     if (cn < nb) {
       c_reg = __ldg(p.c_init + (size_t)(b0 + cn) * kH + S0 + chh);
-      p.Cs[(size_t)(b0 + cn) * kH + S0 + chh] = c_reg;
+      if (!GREEDY) p.Cs[(size_t)(b0 + cn) * kH + S0 + chh] = c_reg;
     }
   }
+  int my_len = 0, my_steps = 0;   // greedy bookkeeping of thread n < kNB
   float bs0 = 0.f, bs1 = 0.f;   // sum over steps of beta[warp][lane], beta[warp][lane + 32]
   // Xe prefetch for the gate outputs this lane owns after its stage-A tile: rows lr0, lr0+8 x examples nF, nF+1
   const bool gate0 = roleA && lr0 >= 2 * kHS && lr0 < 6 * kHS, gate1 = roleA && lr0 + 8 >= 2 * kHS && lr0 + 8 < 6 * kHS;
@@ -435,13 +476,14 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       if (gate1 && nF + m < nb) xe[2 + m] = __ldg(p.Xe + (rowbase + nF + m) * H4 + xe_col1);
     }
   };
-  load_xe((size_t)b0);
+  if (!GREEDY) load_xe((size_t)b0);
   // all CTAs of the cluster must have initialised their barriers and buffers before any remote store
   __syncthreads();
   cluster_barrier();
 
   const uint32_t bytes_xT = (uint32_t)(kC * kNB * Ti * 4), bytes_vec = (uint32_t)(kNB * kH * 4),
                  bytes_xV = (uint32_t)(kC * kNB * kM * 4);
+  int t_last = -1;   // greedy: the step at which every sequence of this cluster had ended
 
   for (int t = 0; t < p.T; ++t) {
     const size_t row0 = (size_t)t * B + b0;   // + n
@@ -454,6 +496,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       mbar_arm(bar0 + 8u * 2, bytes_xV);
       mbar_arm(bar0 + 8u * 3, bytes_vec);
       if (t + 1 < p.T) mbar_arm(bar0 + 8u * 4, bytes_vec);
+      if (GREEDY) mbar_arm(bar0 + 8u * 5, (uint32_t)(kC * kNB * p.V * 4));
     }
     GSCAN3_STAMP(1);
     // ---- stage A: everything that depends only on h_{t-1} ---------------------------------------------
@@ -466,22 +509,22 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         const int type = lr / kHS, i = lr - type * kHS;
         if (type == 0) {
           qT_s[n * kHS + i] = o[j];
-          if (n < nb) p.qT[(row0 + n) * kH + S0 + i] = o[j];
+          if (!GREEDY && n < nb) p.qT[(row0 + n) * kH + S0 + i] = o[j];
         } else if (type == 1) {
           if (COND) {
             ch_s[n * kHS + i] = o[j];
           } else {
             qV_s[n * kHS + i] = o[j];
-            if (n < nb) {
+            if (!GREEDY && n < nb) {
               p.qV[(row0 + n) * kH + S0 + i] = o[j];
               p.Qp[(row0 + n) * kH + S0 + i] = hfull_s[n * kXS + S0 + i];
             }
           }
         } else if (type < 6) {
-          g_s[n * kGS + lr - 2 * kHS] = o[j] + xe[j];
+          g_s[n * kGS + lr - 2 * kHS] = o[j] + (GREEDY ? xeTab_s[tok_s[n] * kG4 + lr - 2 * kHS] : xe[j]);
         }
       }
-      if (t + 1 < p.T) load_xe(row0 + B);
+      if (!GREEDY && t + 1 < p.T) load_xe(row0 + B);
     }
     __syncthreads();
     GSCAN3_STAMP(2);
@@ -505,7 +548,9 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       const float a = e * (1.0f / sum);
       if (lane < Ti) {
         al_s[n * Ti + lane] = a;
-        if (n < nb && rank == n % kC) p.alpha[(row0 + n) * Ti + lane] = a;
+        if (!GREEDY && n < nb && rank == n % kC) p.alpha[(row0 + n) * Ti + lane] = a;
+        if (GREEDY && p.g_alphas && n < nb && rank == n % kC && alive_s[n])
+          p.g_alphas[((size_t)(b0 + n) * p.T + t) * Ti + lane] = a;
       }
     }
     __syncthreads();
@@ -532,12 +577,14 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         const uint32_t off = (uint32_t)(L.qpfull + n * kXS + S0 + 4 * q) * 4u;
 #pragma unroll
         for (int d = 0; d < kC; ++d) st_async_f32x4(rb[d] + off, qq, rb[d] + boff + 8u * 1);
-        if (n < nb) *reinterpret_cast<float4*>(p.Qp + (row0 + n) * kH + S0 + 4 * q) = qq;
+        if (!GREEDY && n < nb) *reinterpret_cast<float4*>(p.Qp + (row0 + n) * kH + S0 + 4 * q) = qq;
       } else if (q < QB) {
         float4* gp = reinterpret_cast<float4*>(g_s + n * kGS + 4 * q - (COND ? kHS : 0));
         float4 gv = *gp;
         gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
         *gp = gv;
+      } else if (GREEDY) {
+        *reinterpret_cast<float4*>(u_s + n * 3 * kHS + kHS + 4 * (q - QB)) = o;
       } else if (n < nb) {
         *reinterpret_cast<float4*>(p.U + (row0 + B + n) * H4 + 2 * kH + S0 + 4 * (q - QB)) = o;
       }
@@ -555,7 +602,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
           const int r = lr0 + 8 * (j >> 1), n = nF + (j & 1);
           if (r < kHS) {
             qV_s[n * kHS + r] = o[j];
-            if (n < nb) p.qV[(row0 + n) * kH + S0 + r] = o[j];
+            if (!GREEDY && n < nb) p.qV[(row0 + n) * kH + S0 + r] = o[j];
           }
         }
       }
@@ -581,15 +628,21 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       const float e0 = __expf(s0 - mx), e1 = (lane < kM - 32) ? __expf(s1 - mx) : 0.f;
       const float inv = 1.0f / warp_sum(e0 + e1);
       const float w0 = e0 * inv, w1 = e1 * inv;
+      const bool counted = !GREEDY || alive_s[n] != 0;   // predict.py sums beta over generated steps only
       be_s[n * kM + lane] = w0;
-      bs0 += w0;
+      if (counted) bs0 += w0;
       if (lane < kM - 32) {
         be_s[n * kM + 32 + lane] = w1;
-        bs1 += w1;
+        if (counted) bs1 += w1;
       }
-      if (n < nb && rank == n % kC) {
+      if (!GREEDY && n < nb && rank == n % kC) {
         p.beta[(row0 + n) * kM + lane] = w0;
         if (lane < kM - 32) p.beta[(row0 + n) * kM + 32 + lane] = w1;
+      }
+      if (GREEDY && p.g_betas && n < nb && rank == n % kC && counted) {
+        float* gb = p.g_betas + ((size_t)(b0 + n) * p.T + t) * kM;
+        gb[lane] = w0;
+        if (lane < kM - 32) gb[32 + lane] = w1;
       }
     }
     __syncthreads();
@@ -616,7 +669,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       const uint32_t off = (uint32_t)(L.cvfull + n * kXS + S0 + 4 * hq) * 4u;
       st_async_f32x4(rb_u + off, o, rb_u + boff + 8u * 3);
       if (u == 0) st_async_f32x4(rb_4 + off, o, rb_4 + boff + 8u * 3);
-      if (u == 1 && n < nb) *reinterpret_cast<float4*>(p.U + (row0 + B + n) * H4 + 3 * kH + S0 + 4 * hq) = o;
+      if (GREEDY) {
+        if (u == 1) *reinterpret_cast<float4*>(u_s + n * 3 * kHS + 2 * kHS + 4 * hq) = o;
+      } else if (u == 1 && n < nb) {
+        *reinterpret_cast<float4*>(p.U + (row0 + B + n) * H4 + 3 * kH + S0 + 4 * hq) = o;
+      }
     }
     GSCAN3_STAMP(11);
     mbar_wait(bar0 + 8u * 3, par);
@@ -640,7 +697,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
 #pragma unroll
         for (int d = 0; d < kC; ++d) st_async_f32(rb[d] + off, hn, rb[d] + boff + 8u * 4);
       }
-      if (cn < nb) {
+      if (GREEDY) u_s[cn * 3 * kHS + chh] = hn;
+      if (!GREEDY && cn < nb) {
         const size_t row = row0 + cn;
         float* go = p.gates + row * H4 + S0 + chh;
         go[0] = ig; go[kH] = fg; go[2 * kH] = gg; go[3 * kH] = og;
@@ -649,7 +707,83 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     GSCAN3_STAMP(14);
+    if (GREEDY) {
+      // ---- logits = OutE[tok] + Wout[:, H:4H] . [h; c_T; c_V]: partial sums over this CTA's slices (X7), argmax, feed back ----
+      __syncthreads();
+      const int V = p.V, Vp = p.Vp;
+      const int total = kNB * V * 4;
+      for (int base = warp * 32; base < total; base += kThreads) {
+        const int item = base + lane, pair = item >> 2, u = item & 3;
+        float s = 0.f;
+        if (item < total) {
+          const int n = pair / V, v = pair - n * V;
+          const float* up = u_s + n * 3 * kHS + 15 * u;
+          const float* wp = wo_s + (15 * u) * Vp + v;
+#pragma unroll
+          for (int i = 0; i < 15; ++i) s = fmaf(up[i], wp[i * Vp], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (item < total) {
+          const uint32_t off = (uint32_t)(L.xL + rank * kNB * V + pair) * 4u;
+          st_async_f32(rb_u + off, s, rb_u + boff + 8u * 5);
+          if (u == 0) st_async_f32(rb_4 + off, s, rb_4 + boff + 8u * 5);
+        }
+      }
+      mbar_wait(bar0 + 8u * 5, par);
+      if (tid < kNB) {
+        const int n = tid;
+        if (alive_s[n]) {
+          const int tok = tok_s[n];
+          float l[32];   // V <= 32 in greedy mode (checked on the host)
+          float mx = -INFINITY;
+          for (int v = 0; v < V; ++v) {
+            float a = outE_s[tok * V + v];
+#pragma unroll
+            for (int r = 0; r < kC; ++r) a += xL_s[(r * kNB + n) * V + v];
+            l[v] = a;
+            mx = fmaxf(mx, a);
+          }
+          float sum = 0.f;
+          for (int v = 0; v < V; ++v) sum += expf(l[v] - mx);
+          const float lse = logf(sum);
+          float best = -INFINITY;   // first maximum of the log-softmax values, as F.log_softmax(...).max(dim=-1) gives
+          int arg = 0;
+          for (int v = 0; v < V; ++v) {
+            const float lp = (l[v] - mx) - lse;
+            if (lp > best) { best = lp; arg = v; }
+          }
+          my_steps++;
+          if (arg == p.eos) {
+            alive_s[n] = 0;
+          } else {
+            if (rank == 0) p.out_tokens[(size_t)(b0 + n) * p.T + my_len] = arg;
+            my_len++;
+          }
+          tok_s[n] = arg;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int any = 0;
+        for (int n = 0; n < kNB; ++n) any |= alive_s[n];
+        flag_s[0] = any;
+      }
+      __syncthreads();
+      if (!flag_s[0]) {   // the same decision in every CTA of the cluster: all of them computed the same tokens
+        t_last = t;
+        break;
+      }
+    }
     GSCAN3_STAMP(15);
+  }
+  if (GREEDY) {
+    // stores of h_t towards this CTA issued in the last executed step must land before it may exit
+    if (t_last >= 0 && t_last + 1 < p.T) mbar_wait(bar0 + 8u * 4, (uint32_t)(t_last & 1));
+    if (rank == 0 && tid < nb) {
+      p.out_len[b0 + tid] = my_len;
+      p.out_steps[b0 + tid] = my_steps;
+    }
   }
 
   if (warp < nb && rank == warp % kC) {

@@ -220,14 +220,19 @@ __global__ void __launch_bounds__(GTHREADS, 2) sgemm_kernel(GemmP p) {
           bl[nt][c] = __float_as_uint(v[c] - __uint_as_float(bh[nt][c]));
         }
       }
+      // term-major order: 8 independent accumulators between two dependent MMAs
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          gemm_mma_tf32(tmp[mt][nt], al[mt], bh[nt]);
-          gemm_mma_tf32(tmp[mt][nt], ah[mt], bl[nt]);
-          gemm_mma_tf32(tmp[mt][nt], ah[mt], bh[nt]);
-        }
+        for (int nt = 0; nt < 4; ++nt) gemm_mma_tf32(tmp[mt][nt], al[mt], bh[nt]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) gemm_mma_tf32(tmp[mt][nt], ah[mt], bl[nt]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) gemm_mma_tf32(tmp[mt][nt], ah[mt], bh[nt]);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i)

@@ -503,12 +503,12 @@ int launch_dec_fwd_cluster(const gscan_dims& d, const float* const* P, float* ws
 
 
 // ---- register-resident cluster sweep (v3, decoder_v3.cuh): H = 100, 6x6 grid only ---------------------
-template <bool COND>
+template <bool COND, bool GREEDY>
 int v3_fwd_prepare(size_t bytes) {
   static bool done = false, ok = false;
   static size_t done_bytes = 0;
   if (done && bytes <= done_bytes) return ok ? 0 : GSCAN_E_UNSUPPORTED;
-  auto kern = v3::dec_fwd_v3_kernel<COND>;
+  auto kern = v3::dec_fwd_v3_kernel<COND, GREEDY>;
   ok = false;
   done = true;
   done_bytes = bytes;
@@ -569,25 +569,31 @@ void print_timeline(const char* what, long long* tl, int T, cudaStream_t st) {
 }
 
 int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, const Layout& L, v3::DecFwd3P p,
-                      cudaStream_t st) {
+                      bool greedy, cudaStream_t st) {
   const int cond = d.conditional_attention ? 1 : 0;
-  const v3::FwdSmem sm = v3::fwd_smem(d.Ti, cond);
+  const v3::FwdSmem sm = v3::fwd_smem(d.Ti, cond, greedy ? d.V : 0);
   const size_t bytes = (size_t)sm.total * sizeof(float);
   if (bytes > kMaxSmemBytes) return GSCAN_E_UNSUPPORTED;
-  TRY(cond ? v3_fwd_prepare<true>(bytes) : v3_fwd_prepare<false>(bytes));
+  if (greedy) TRY(cond ? (v3_fwd_prepare<true, true>(bytes)) : (v3_fwd_prepare<false, true>(bytes)));
+  else TRY(cond ? (v3_fwd_prepare<true, false>(bytes)) : (v3_fwd_prepare<false, false>(bytes)));
   TRY(compute_PT(d, P, p.KT, ws + L.PT, L.RB, st));
   p.PT = ws + L.PT;
   p.W_qT = P[GSCAN_P_TXT_QUERY_W]; p.W_c = P[GSCAN_P_COND_W]; p.W_hh = P[GSCAN_P_DEC_WHH];
   p.W_qV = P[GSCAN_P_VIS_QUERY_W]; p.W_ih = P[GSCAN_P_DEC_WIH];
   static const bool want_timeline = getenv("GSCAN_TIMELINE") != nullptr;   // debug only: allocates and synchronises
   long long* tl = nullptr;
-  if (want_timeline) {
+  if (want_timeline && !greedy) {
     cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
     p.timeline = tl;
   }
   const int grid = ceil_div(d.B, v3::kNB) * v3::kC;
-  if (cond) v3::dec_fwd_v3_kernel<true><<<grid, v3::kThreads, bytes, st>>>(p);
-  else v3::dec_fwd_v3_kernel<false><<<grid, v3::kThreads, bytes, st>>>(p);
+  if (greedy) {
+    if (cond) v3::dec_fwd_v3_kernel<true, true><<<grid, v3::kThreads, bytes, st>>>(p);
+    else v3::dec_fwd_v3_kernel<false, true><<<grid, v3::kThreads, bytes, st>>>(p);
+  } else {
+    if (cond) v3::dec_fwd_v3_kernel<true, false><<<grid, v3::kThreads, bytes, st>>>(p);
+    else v3::dec_fwd_v3_kernel<false, false><<<grid, v3::kThreads, bytes, st>>>(p);
+  }
   GSCAN_CHECK_LAUNCH();
   if (tl) print_timeline("v3 fwd", tl, p.T, st);
   return 0;
@@ -765,7 +771,7 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
     p3.KT = p.KT; p3.KV = p.KV; p3.cmd_len = cmd_len; p3.h_init = p.h_init; p3.c_init = p.c_init; p3.Xe = p.Xe;
     p3.U = p.U; p3.Cs = p.Cs; p3.gates = p.gates; p3.alpha = p.alpha; p3.beta = p.beta;
     p3.Qp = p.Qp; p3.qT = p.qT; p3.qV = p.qV; p3.beta_sum = p.beta_sum;
-    int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, st);
+    int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, false, st);
     if (rc == 0) v3_done = true;
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
   }
@@ -1088,7 +1094,21 @@ int gscan_greedy_decode(const gscan_dims* d, const float* const* P, const int64_
   p.out_tokens = reinterpret_cast<long long*>(out_tokens);
   p.out_len = out_len; p.out_steps = out_steps;
   p.g_alphas = alphas; p.g_betas = betas;
-  TRY(launch_dec_fwd(e, p, true, st));
+  bool greedy_v3 = false;
+  if (v3_shape_ok(e) && V <= 32 && !getenv("GSCAN_GREEDY_V1")) {
+    v3::DecFwd3P p3{};
+    p3.B = B; p3.T = T; p3.Ti = e.Ti;
+    p3.vT = p.vT; p3.vV = p.vV; p3.bc = p.bc;
+    p3.KT = p.KT; p3.KV = p.KV; p3.cmd_len = cmd_len; p3.h_init = p.h_init; p3.c_init = p.c_init;
+    p3.beta_sum = beta_sum;
+    p3.XeTab = XeTab; p3.OutE = OutE; p3.Wo_t = Wo_t; p3.V = V; p3.Vp = Vp; p3.sos = sos; p3.eos = eos;
+    p3.out_tokens = p.out_tokens; p3.out_len = out_len; p3.out_steps = out_steps;
+    p3.g_alphas = alphas; p3.g_betas = betas;
+    int rc = launch_dec_fwd_v3(e, P, ws, L, p3, true, st);
+    if (rc == 0) greedy_v3 = true;
+    else if (rc != GSCAN_E_UNSUPPORTED) return rc;
+  }
+  if (!greedy_v3) TRY(launch_dec_fwd(e, p, true, st));
   if (aux_logp) {
     row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(beta_sum, M, B, aux_logp);
     GSCAN_CHECK_LAUNCH();
