@@ -16,10 +16,11 @@ all-reduce when N>1) + Adam.  Rank 0 prints ONE JSON line.
   e2e       the same step driven from pinned HOST buffers through the public API
             (Model/FusedTrainer): H2D copies of the batch and a D2H read of the loss inside the
             timed region, wall clock with a device synchronize at both ends.
-  roofline  the dominant kernel (decoder backward sweep) timed live with CUDA events recorded by the
-            library on the same stream (gscan_profile); the sweep is an fp32 FMA-pipe, latency-bound
-            recurrence, so its fraction of the measured bf16 tensor peak is tiny by construction -
-            the object also carries the fp32 FMA-pipe fraction and microseconds per decoder step.
+  roofline  the dominant kernel (decoder backward cluster sweep) timed live with CUDA events recorded by
+            the library on the same stream (gscan_profile); the sweep is a latency / synchronisation bound
+            recurrence (121 dependent steps), so its fraction of the measured bf16 tensor peak is tiny by
+            construction - the object also carries microseconds per decoder step, the fraction of the
+            mma.sync tf32 ceiling, and the DRAM traffic per launch from the committed ncu capture.
   cpu_baseline / --impl reference
             the CPU port of the reference (oracle/gscan_oracle.py: same per-step PyTorch-eager
             structure) on all host cores, same shape, same step definition.  /root/reference itself
@@ -69,6 +70,15 @@ def read_peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "sm_max_mhz": p.get("sm_max_mhz", 1965.0),
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+def read_ncu_profile():
+    """DRAM bytes per launch of the two sweeps from the committed `ncu --set full` capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r01_v3_ncu_sweeps.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
 
 
 class ClockSampler:
@@ -331,19 +341,28 @@ def main():
         peaks = read_peaks()
         Tt = host["targets"].shape[1]
         bwd_ms = stages["dec_bwd_sweep"]
+        fwd_ms = stages["dec_fwd_sweep"]
         achieved_tflops = B_PER_GPU * Tt * SWEEP_BWD_FLOP / (bwd_ms * 1e-3) / 1e12
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks["sm_max_mhz"]
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        # legacy tensor path (mma.sync m16n8k8 tf32): 512 MAC/clk/SM measured (tools/ubench_mma.cu); the sweeps
+        # spend 3 MMAs per fp32-accurate product (3xTF32), so the fp32-equivalent ceiling is a third of that
+        tf32_mma_peak = 148 * 512 * 2 * sm_mhz * 1e6 / 1e12
+        ncu = read_ncu_profile()
         roofline = {
-            "kernel": "decoder_bwd_kernel (BPTT sweep over all 121 steps)", "bound": "tensor",
+            "kernel": "v3::dec_bwd_v3_kernel (BPTT cluster sweep over all 121 steps, one launch)", "bound": "tensor",
             "achieved": achieved_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-            "frac": achieved_tflops / peaks["bf16_tflops"], "peak_source": peaks["source"], "traffic": None,
-            "note": "fp32 FMA-pipe recurrence (1e-4 parity rules out bf16 operands): latency/issue bound, "
-                    "not tensor or HBM bound; see frac_fp32_fma and us_per_decoder_step",
-            "fp32_fma_peak_tflops": fp32_peak, "frac_fp32_fma": achieved_tflops / fp32_peak,
+            "frac": achieved_tflops / peaks["bf16_tflops"], "peak_source": peaks["source"],
+            "traffic": ncu.get("bwd_dram_bytes"),
+            "note": "recurrence: 121 dependent steps x ~12 dependent phases; latency/synchronisation bound, not tensor or "
+                    "HBM bound (ncu: tensor pipe ~7 % active, issue slots ~40 % busy, 27 % of stall samples at block "
+                    "barriers).  Figure of merit: us_per_decoder_step.  Mat-vecs run on mma.sync tf32 in split "
+                    "precision (3 MMAs per fp32-accurate product).",
+            "mma_sync_tf32_peak_tflops": tf32_mma_peak, "frac_mma_sync_tf32_3x": 3 * achieved_tflops / tf32_mma_peak,
             "kernel_ms": bwd_ms, "us_per_decoder_step": 1e3 * bwd_ms / Tt,
-            "fwd_sweep_ms": stages["dec_fwd_sweep"], "fwd_us_per_decoder_step": 1e3 * stages["dec_fwd_sweep"] / Tt,
-            "fwd_frac_fp32_fma": B_PER_GPU * Tt * SWEEP_FWD_FLOP / (stages["dec_fwd_sweep"] * 1e-3) / 1e12 / fp32_peak,
+            "fwd_kernel": "v3::dec_fwd_v3_kernel", "fwd_sweep_ms": fwd_ms, "fwd_us_per_decoder_step": 1e3 * fwd_ms / Tt,
+            "fwd_achieved_tflops": B_PER_GPU * Tt * SWEEP_FWD_FLOP / (fwd_ms * 1e-3) / 1e12,
+            "fwd_traffic": ncu.get("fwd_dram_bytes"),
+            "ncu": ncu.get("summary"),
             "stage_ms": stages,
             "whole_step_tflops": value * STEP_FLOP_PER_EXAMPLE / 1e12,
         }

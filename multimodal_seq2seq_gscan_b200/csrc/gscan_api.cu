@@ -878,6 +878,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
   }
   if (bwd_v3) {
+    prof_mark(7, st);   // the sweep kernel alone; what follows counts as batched weight-gradient work
     // value path of both attentions, outside the recurrence: dc_T, dc_V for all steps as batched products,
     // accumulated into the (already consumed) [c_T | c_V] columns of dU, then dK += sum_t w_t dc_t
     TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH] + H, 3 * H, ws + L.dU + 2 * H, 4 * H, R, 2 * H, 4 * H, 1, st));
@@ -890,8 +891,8 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     GSCAN_CHECK_LAUNCH();
   } else {
     TRY(launch_dec_bwd(*d, bp, st));
+    prof_mark(7, st);
   }
-  prof_mark(7, st);
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   // B5: decoder weight gradients as batched "TN" products over all steps
