@@ -1,0 +1,459 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores (tcgen05, kind::tf32) for the large batched
+// contractions of the path: the output projection over all decoder steps, the input-gate pre-GEMM,
+// the data gradients of those, and every decoder weight gradient (split-K "TN" products with
+// K = Tt*B = 24,200).  Same contract as sgemm_kernel (gemm.cuh):
+//
+//   C[i,j] (ldc) (+)= act( sum_k A(i,k) * B(k,j) + bias[j] + bias2[j] )
+//
+// with each operand contiguous along one axis (K-major or MN-major); both majors are consumed
+// directly from the layout TMA lands them in (128-byte swizzle), so nothing is transposed in HBM.
+//
+// Arithmetic: 3xTF32.  The operands are fp32 activations / gradients produced on the fly, so the
+// hi / lo split happens in shared memory: TMA lands the raw fp32 tile, four converter warps rewrite it
+// in place as hi = rn_tf32(x) and write lo = rn_tf32(x - hi) to a twin buffer at the SAME byte offset
+// (element-wise, hence swizzle-agnostic), and the MMA thread issues lo*hi + hi*lo + hi*hi into one
+// TMEM accumulator.  The dropped lo*lo term is ~2^-22 relative.
+//
+// Persistent kernel, one CTA per SM walking a static tile list (m-tile, n-tile, k-split).
+// Roles (320 threads, 3-stage ring of 64 KB stages, two TMEM accumulator buffers):
+//   warp 0      TMA producer        empty[s]    -> full_raw[s] (expect_tx)
+//   warps 2-5   hi/lo converters    full_raw[s] -> full_cvt[s] (fence.proxy.async + arrive)
+//   warp 1      MMA issuer          full_cvt[s], acc_empty[b] -> tcgen05.mma x12 -> tcgen05.commit -> empty[s], acc_full[b]
+//   warps 6-9   accumulate/epilogue acc_full[b] -> tcgen05.ld -> fp32 RN add into registers -> acc_empty[b];
+//                                   after the last K-block: bias/act -> coalesced global stores (atomicAdd for split-K)
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace gscan {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32;          // BK fp32 = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;              // 16 KB (A and B tiles have the same size: BM == BN)
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_hi | A_lo | B_hi | B_lo
+constexpr int THREADS = 320;
+constexpr int CVT_THREADS = 128;
+constexpr int EPI_THREADS = 128;
+constexpr int FLUSH = 1;                             // K-blocks accumulated in TMEM before the sum is folded into registers
+constexpr int TMEM_COLS = 2 * BN;                    // two accumulator buffers
+constexpr int EPI_BYTES = 4 * 32 * 33 * 4;           // per-warp 32x33 transpose tiles for the write-out
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct Params {
+  float* C; long ldc;
+  int M, N, K;
+  const float* bias; const float* bias2;
+  int act;          // 0 none, 1 tanh, 2 relu
+  int accumulate;   // C += result (single split only)
+  int kb_per;       // K-blocks per split
+  int kb_total;
+  int ksplit;
+  uint32_t mn_layout, mn_sbo, mn_lbo;   // descriptor fields of an MN-major operand
+};
+// MN-major tf32 operands exist only in the 32-byte-atom flavour of the 128-byte swizzle (layout type 1, TMA
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4 k-rows of 128 B per swizzle atom, atoms SBO = 512 B apart.
+struct MnConfig { uint32_t layout = 1, sbo = 512, lbo = BK * 128; int tma_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; };
+inline MnConfig& mn_config() { static MnConfig c; return c; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1", 128-byte swizzle).
+//   K-major : rows of 128 B (32 fp32 of K), 8-row swizzle atoms 1024 B apart (SBO); LBO unused.
+//             One MMA consumes K = 8 fp32 = 32 B: advance the start address by 32 B per k-step.
+//   MN-major: rows of 128 B (32 fp32 of M/N) per k; 8 k-rows = one 1024-B atom (SBO between atoms);
+//             the next 32 M/N elements start LBO = BK*128 B later (one TMA box per 32 columns).
+//             One MMA consumes 8 k-rows = one atom: advance the start address by 1024 B per k-step.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)layout << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+// instruction descriptor: D fp32, A/B tf32, M = 128, N = n (multiple of 16), majors as given
+__host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t tf32_rn_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+
+template <bool AK, bool BKM>   // operand contiguous along K in global memory (else along M / N)
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t base = (smem_u32(tc_smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = tc_smem_raw + (base - smem_u32(tc_smem_raw));
+  const uint32_t bar0 = base + STAGES * STAGE_BYTES + EPI_BYTES;
+  auto full_raw = [&](int s) { return bar0 + 8u * s; };
+  auto full_cvt = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (3 * STAGES + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (3 * STAGES + 2 + b); };
+  const uint32_t tmem_slot = bar0 + 8u * (3 * STAGES + 4);
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_raw(s), 1);
+      mbar_init(full_cvt(s), CVT_THREADS);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full(b), 1);
+      mbar_init(acc_empty(b), EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  // persistent static schedule: tile = ((m-tile * n_tiles + n-tile) * ksplit + z); every role walks the same list
+  const int n_tiles = ceil_div(p.N, BN);
+  const int total_tiles = ceil_div(p.M, BM) * n_tiles * p.ksplit;
+  auto tile_coords = [&](int tile, int& m0, int& n0, int& kb0, int& nkb) {
+    const int z = tile % p.ksplit;
+    const int mn = tile / p.ksplit;
+    m0 = (mn / n_tiles) * BM;
+    n0 = (mn % n_tiles) * BN;
+    kb0 = z * p.kb_per;
+    nkb = min(p.kb_total, kb0 + p.kb_per) - kb0;
+  };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        tile_coords(tile, m0, n0, kb0, nkb);
+        for (int it = 0; it < nkb; ++it, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
+          const uint32_t st = base + s * STAGE_BYTES;
+          const int k = (kb0 + it) * BK;
+          mbar_arrive_expect_tx(full_raw(s), 2 * TILE_BYTES);
+          if (AK) {
+            tma_load_2d(st, &tmA, k, m0, full_raw(s));                       // box [32 k][128 rows]
+          } else {
+#pragma unroll
+            for (int q = 0; q < BM / 32; ++q)                                // 4 boxes [32 m][32 k]
+              tma_load_2d(st + q * (BK * 128), &tmA, m0 + 32 * q, k, full_raw(s));
+          }
+          if (BKM) {
+            tma_load_2d(st + 2 * TILE_BYTES, &tmB, k, n0, full_raw(s));
+          } else {
+#pragma unroll
+            for (int q = 0; q < BN / 32; ++q)
+              tma_load_2d(st + 2 * TILE_BYTES + q * (BK * 128), &tmB, n0 + 32 * q, k, full_raw(s));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      int g = 0, w = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        tile_coords(tile, m0, n0, kb0, nkb);
+        const int n_valid = min(BN, p.N - n0);
+        const uint32_t idesc = make_idesc(!AK, !BKM, min(BN, (n_valid + 15) & ~15));
+        int in_win = 0;
+        for (int it = 0; it < nkb; ++it, ++g) {
+          const int s = g % STAGES;
+          const uint32_t tacc = tmem_base + (uint32_t)((w & 1) * BN);
+          if (in_win == 0) {   // the accumulate warps must have drained this TMEM buffer (two windows ago)
+            mbar_wait(acc_empty(w & 1), ((w >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          mbar_wait(full_cvt(s), (g / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t st = base + s * STAGE_BYTES;
+          const uint32_t a_hi = st, a_lo = st + TILE_BYTES, b_hi = st + 2 * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 8; ++k) {
+            const uint32_t ao = AK ? 32u * k : 1024u * k, bo = BKM ? 32u * k : 1024u * k;
+            const uint32_t a_lbo = AK ? 16u : p.mn_lbo, b_lbo = BKM ? 16u : p.mn_lbo;
+            const uint32_t a_sbo = AK ? 1024u : p.mn_sbo, b_sbo = BKM ? 1024u : p.mn_sbo;
+            const uint32_t a_lay = AK ? 2u : p.mn_layout, b_lay = BKM ? 2u : p.mn_layout;
+            const uint64_t dah = make_desc(a_hi + ao, a_lbo, a_sbo, a_lay), dal = make_desc(a_lo + ao, a_lbo, a_sbo, a_lay);
+            const uint64_t dbh = make_desc(b_hi + bo, b_lbo, b_sbo, b_lay), dbl = make_desc(b_lo + bo, b_lbo, b_sbo, b_lay);
+            mma_tf32(tacc, dal, dbh, idesc, (in_win > 0 || k > 0) ? 1u : 0u);   // small terms first
+            mma_tf32(tacc, dah, dbl, idesc, 1u);
+            mma_tf32(tacc, dah, dbh, idesc, 1u);
+          }
+          mma_commit(empty(s));               // frees the stage once these MMAs have read it
+          ++in_win;
+          if (in_win == FLUSH || it == nkb - 1) {
+            mma_commit(acc_full(w & 1));      // window complete: hand the TMEM buffer to the accumulate warps
+            ++w;
+            in_win = 0;
+          }
+        }
+      }
+    }
+  } else if (warp < 2 + CVT_THREADS / 32) {
+    // ===== hi / lo converters (warps 2..5) =====
+    const int ct = threadIdx.x - 64;
+    int g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m0, n0, kb0, nkb;
+      tile_coords(tile, m0, n0, kb0, nkb);
+      for (int it = 0; it < nkb; ++it, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(full_raw(s), (g / STAGES) & 1);
+        uint8_t* st = gen_base + (size_t)s * STAGE_BYTES;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {   // A then B
+          float4* hi = reinterpret_cast<float4*>(st + half * 2 * TILE_BYTES);
+          float4* lo = reinterpret_cast<float4*>(st + half * 2 * TILE_BYTES + TILE_BYTES);
+          float4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = hi[ct + i * CVT_THREADS];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 h, l;
+            h.x = __uint_as_float(tf32_rn_bits(v[i].x)); l.x = __uint_as_float(tf32_rn_bits(v[i].x - h.x));
+            h.y = __uint_as_float(tf32_rn_bits(v[i].y)); l.y = __uint_as_float(tf32_rn_bits(v[i].y - h.y));
+            h.z = __uint_as_float(tf32_rn_bits(v[i].z)); l.z = __uint_as_float(tf32_rn_bits(v[i].z - h.z));
+            h.w = __uint_as_float(tf32_rn_bits(v[i].w)); l.w = __uint_as_float(tf32_rn_bits(v[i].w - h.w));
+            hi[ct + i * CVT_THREADS] = h;
+            lo[ct + i * CVT_THREADS] = l;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA (async proxy)
+        mbar_arrive(full_cvt(s));
+      }
+    }
+  } else {
+    // ===== accumulate + epilogue (warps 6..9) =====
+    // thread = one accumulator row (TMEM lane); a warp may only touch lanes 32*(warp%4)..+31.  The tensor core adds
+    // into its fp32 accumulator with truncation, so every FLUSH K-blocks the window sum is folded into registers
+    // with round-to-nearest adds (same policy as sgemm_kernel).
+    const int q = warp & 3;
+    float* stage_out = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES) + (warp - 6) * (32 * 33);
+    const bool split = p.ksplit > 1;
+    int w = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m0, n0, kb0, nkb;
+      tile_coords(tile, m0, n0, kb0, nkb);
+      const int n_valid = min(BN, p.N - n0);
+      const int nwin = ceil_div(nkb, FLUSH);
+      float acc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+      for (int i = 0; i < nwin; ++i, ++w) {
+        mbar_wait(acc_full(w & 1), (w >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((w & 1) * BN);
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          if (c * 32 < n_valid) {            // warp-uniform
+            uint32_t v[32];
+            tmem_ld32(tacc + (uint32_t)(c * 32), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c * 32 + j] += __uint_as_float(v[j]);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(acc_empty(w & 1));
+      }
+      // write-out: per-warp 32x32 transpose through shared memory so that every global access is a full 128-B row segment
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 < n_valid) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stage_out[lane * 33 + j] = acc[c * 32 + j];
+          __syncwarp();
+          const int gn = n0 + c * 32 + lane;
+          float bsum = 0.f;
+          if (!split && gn < p.N) {
+            if (p.bias) bsum += __ldg(p.bias + gn);
+            if (p.bias2) bsum += __ldg(p.bias2 + gn);
+          }
+          if (gn < p.N) {
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+              const int gm = m0 + 32 * q + r;
+              if (gm >= p.M) break;
+              float val = stage_out[r * 33 + lane];
+              float* dst = p.C + (long)gm * p.ldc + gn;
+              if (split) {
+                atomicAdd(dst, val);
+              } else {
+                val += bsum;
+                if (p.act == 1) val = act_tanh(val);
+                else if (p.act == 2) val = fmaxf(val, 0.f);
+                if (p.accumulate) val += *dst;
+                *dst = val;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: `inner` contiguous elements per row, `outer` rows `ld` floats apart; box [box_inner=32][box_outer]
+inline int make_map(CUtensorMap* m, const float* ptr, long inner, long outer, long ld, int box_outer,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -2;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+inline bool eligible(const float* A, long a_rs, long a_cs, const float* B, long b_rs, long b_cs, int M, int N, int K) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool ak = (a_cs == 1), bk = (b_rs == 1);
+  if ((!ak && a_rs != 1) || (!bk && b_cs != 1)) return false;
+  const long lda = ak ? a_rs : a_cs, ldb = bk ? b_cs : b_rs;
+  if (!al16(A) || !al16(B) || (lda & 3) || (ldb & 3)) return false;
+  if (M < 64 || N < 32 || K < 32) return false;     // tiny products stay on the mma.sync kernel
+  return encode_fn() != nullptr;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool AK, bool BKM>
+inline int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  tc_gemm_kernel<AK, BKM><<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, p);
+  GSCAN_CHECK_LAUNCH();
+  return 0;
+}
+
+// Same argument meaning as launch_sgemm (gemm.cuh).  ksplit > 1 requires C initialised and forbids bias / act.
+inline int launch(const float* A, long a_rs, long a_cs, const float* B, long b_rs, long b_cs, float* C, long ldc,
+                  int M, int N, int K, const float* bias, const float* bias2, int act, int accumulate, int ksplit,
+                  cudaStream_t st) {
+  if (M <= 0 || N <= 0) return 0;
+  const bool ak = (a_cs == 1), bk = (b_rs == 1);
+  const long lda = ak ? a_rs : a_cs, ldb = bk ? b_cs : b_rs;
+  CUtensorMap ta, tb;
+  const MnConfig& mc = mn_config();
+  const CUtensorMapSwizzle mn_swz = (CUtensorMapSwizzle)mc.tma_swizzle;
+  int rc = ak ? make_map(&ta, A, K, M, lda, BM) : make_map(&ta, A, M, K, lda, BK, mn_swz);
+  if (rc) return rc;
+  rc = bk ? make_map(&tb, B, K, N, ldb, BN) : make_map(&tb, B, N, K, ldb, BK, mn_swz);
+  if (rc) return rc;
+  Params p{C, ldc, M, N, K, bias, bias2, act, accumulate, 0, 0, 1, mc.layout, mc.sbo, mc.lbo};
+  p.kb_total = ceil_div(K, BK);
+  if (ksplit < 1) ksplit = 1;
+  p.kb_per = ceil_div(p.kb_total, ksplit);
+  p.ksplit = ceil_div(p.kb_total, p.kb_per);
+  const int tiles = ceil_div(N, BN) * ceil_div(M, BM) * p.ksplit;
+  dim3 grid(min(tiles, num_sms()));
+  if (ak && bk) return launch_t<true, true>(ta, tb, p, grid, st);
+  if (ak && !bk) return launch_t<true, false>(ta, tb, p, grid, st);
+  if (!ak && bk) return launch_t<false, true>(ta, tb, p, grid, st);
+  return launch_t<false, false>(ta, tb, p, grid, st);
+}
+
+}  // namespace tc
+}  // namespace gscan
