@@ -226,6 +226,14 @@ int gscan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 int gscan_sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
                 float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
                 const float* bias, int32_t act, int32_t accumulate, void* stream);
+/* Same product on an explicitly chosen kernel: path 0 = mma.sync 3xTF32 (gemm.cuh), path 1 = tcgen05 3xTF32 with
+ * TMA-fed operands (gemm_tc.cuh; GSCAN_E_UNSUPPORTED unless both operands are 16-byte aligned with leading dimensions
+ * that are multiples of 4 floats, M >= 64, N >= 32, K >= 32).  ksplit > 1 splits K over CTAs and ADDS the partial sums
+ * into C atomically (C must be initialised; bias / act are then rejected).  gscan_sgemm and the training step choose
+ * the path by size; this entry point exists so that both kernels can be checked against each other. */
+int gscan_sgemm_path(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs,
+                     float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                     const float* bias, int32_t act, int32_t accumulate, int32_t ksplit, int32_t path, void* stream);
 /* ConvolutionalNet.forward (reference cnn_model.py:22-36): feat [B,G*G,3F]. */
 int gscan_cnn_forward(const gscan_dims* d, const float* const* params, const float* situations,
                       const float* drop_cnn, float* workspace, size_t workspace_floats,

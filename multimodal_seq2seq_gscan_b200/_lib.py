@@ -65,6 +65,8 @@ SIGNATURES = {
                                   c_float, c_int32, c_float, c_void_p]),
     "gscan_sgemm": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
                               c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
+    "gscan_sgemm_path": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
+                                   c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "gscan_cnn_forward": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_size_t,
                                     c_void_p, c_void_p]),
 }

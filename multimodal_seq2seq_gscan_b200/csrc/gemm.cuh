@@ -16,6 +16,7 @@
 // would need a separate hi/lo staging pass per operand tile)
 #pragma once
 #include "common.cuh"
+#include "gemm_tc.cuh"
 
 namespace gscan {
 
@@ -306,6 +307,19 @@ inline int launch_sgemm(const float* A, long a_rs, long a_cs, const float* B, lo
   return vec ? launch_sgemm_t<false, true, true>(p, grid, st) : launch_sgemm_t<false, true, false>(p, grid, st);
 }
 
+// Path choice for one product: the tcgen05 kernel (gemm_tc.cuh) when TMA can address both operands and the
+// product is large enough to amortise its pipeline fill; the mma.sync kernel above otherwise.
+inline bool use_tc(const float* A, long a_rs, long a_cs, const float* B, long b_rs, long b_cs, int M, int N, int K) {
+  return (long)M * N * K >= (1L << 26) && tc::eligible(A, a_rs, a_cs, B, b_rs, b_cs, M, N, K);
+}
+inline int launch_gemm(const float* A, long a_rs, long a_cs, const float* B, long b_rs, long b_cs,
+                       float* C, long ldc, int M, int N, int K, const float* bias, const float* bias2,
+                       int act, int accumulate, int ksplit, cudaStream_t st) {
+  if (use_tc(A, a_rs, a_cs, B, b_rs, b_cs, M, N, K))
+    return tc::launch(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, bias, bias2, act, accumulate, ksplit, st);
+  return launch_sgemm(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, bias, bias2, act, accumulate, ksplit, st);
+}
+
 // Weight-gradient form: C[N1,N2] (ldc) = sum_r X[r, i] * Y[r, j] over R rows (R large).
 // Chooses a split so the grid covers the chip; C is zeroed here first.
 inline int launch_grad_gemm(const float* X, long ldx, const float* Y, long ldy, float* C, long ldc,
@@ -313,6 +327,11 @@ inline int launch_grad_gemm(const float* X, long ldx, const float* Y, long ldy, 
   // zero the destination block (it may be a column block of a wider matrix)
   cudaError_t e = cudaMemset2DAsync(C, ldc * sizeof(float), 0, N2 * sizeof(float), N1, st);
   if (e != cudaSuccess) return (int)e;
+  if (use_tc(X, 1, ldx, Y, ldy, 1, N1, N2, R)) {
+    const int tiles = ceil_div(N1, tc::BM) * ceil_div(N2, tc::BN);
+    const int ksplit = max(1, min(ceil_div(R, 4 * tc::BK), num_sms / tiles));   // one persistent wave
+    return tc::launch(X, 1, ldx, Y, ldy, 1, C, ldc, N1, N2, R, nullptr, nullptr, 0, 0, ksplit, st);
+  }
   int tiles = ceil_div(N1, GBM) * ceil_div(N2, GBN);
   int ksplit = max(1, min(ceil_div(R, 4 * GBK), (2 * num_sms) / tiles));   // one wave at 2 CTAs per SM
   return launch_sgemm(X, 1, ldx, Y, ldy, 1, C, ldc, N1, N2, R, nullptr, nullptr, 0, 0, ksplit, st);

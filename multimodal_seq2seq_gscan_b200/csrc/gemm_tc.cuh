@@ -9,10 +9,16 @@
 // directly from the layout TMA lands them in (128-byte swizzle), so nothing is transposed in HBM.
 //
 // Arithmetic: 3xTF32.  The operands are fp32 activations / gradients produced on the fly, so the
-// hi / lo split happens in shared memory: TMA lands the raw fp32 tile, four converter warps rewrite it
-// in place as hi = rn_tf32(x) and write lo = rn_tf32(x - hi) to a twin buffer at the SAME byte offset
-// (element-wise, hence swizzle-agnostic), and the MMA thread issues lo*hi + hi*lo + hi*hi into one
-// TMEM accumulator.  The dropped lo*lo term is ~2^-22 relative.
+// hi / lo split happens in shared memory: TMA lands the raw fp32 tile, which the tensor core reads as
+// hi = trunc_tf32(x) as it is; four converter warps write lo = rn_tf32(x - hi) to a twin buffer at the
+// SAME byte offset (element-wise, hence swizzle-agnostic), and the MMA thread issues lo*hi + hi*lo + hi*hi
+// into a TMEM accumulator.  The dropped lo*lo term is ~2^-20 relative.  The tensor core adds into its fp32
+// accumulator with truncation (measured: error grows linearly with the number of MMAs), so every FLUSH
+// K-blocks the window sum is folded into register accumulators with round-to-nearest adds.
+//
+// What bounds it: shared-memory bandwidth, not the tensor pipe.  Per 128x128x32 K-block the SM moves
+// 32 KB (TMA in) + 64 KB (converter read + lo write) + 96 KB (12 SS-mode MMAs x 8 KB of operand fetch)
+// = 192 KB through a 128 B/clk pipe = 1500 clk, against 768 clk of MMA issue (tools/tc_gemm_dev.cu timeline).
 //
 // Persistent kernel, one CTA per SM walking a static tile list (m-tile, n-tile, k-split).
 // Roles (320 threads, 3-stage ring of 64 KB stages, two TMEM accumulator buffers):
@@ -35,9 +41,13 @@ constexpr int STAGE_BYTES = 4 * TILE_BYTES;          // A_hi | A_lo | B_hi | B_l
 constexpr int THREADS = 320;
 constexpr int CVT_THREADS = 128;
 constexpr int EPI_THREADS = 128;
-constexpr int FLUSH = 1;                             // K-blocks accumulated in TMEM before the sum is folded into registers
-constexpr int TMEM_COLS = 2 * BN;                    // two accumulator buffers
-constexpr int EPI_BYTES = 4 * 32 * 33 * 4;           // per-warp 32x33 transpose tiles for the write-out
+#ifndef GSCAN_TC_FLUSH
+#define GSCAN_TC_FLUSH 2
+#endif
+constexpr int FLUSH = GSCAN_TC_FLUSH;                             // K-blocks accumulated in TMEM before the sum is folded into registers
+constexpr int ACC_BUFS = 4;                          // TMEM accumulator buffers (4 x 128 columns = all of TMEM)
+constexpr int TMEM_COLS = ACC_BUFS * BN;
+constexpr int EPI_BYTES = 4 * 32 * 36 * 4;           // per-warp 32x36 transpose tiles for the write-out
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct Params {
@@ -50,10 +60,19 @@ struct Params {
   int kb_total;
   int ksplit;
   uint32_t mn_layout, mn_sbo, mn_lbo;   // descriptor fields of an MN-major operand
+  long long* timeline;                  // optional [4 roles][128] clock64 stamps of CTA 0 (tools/tc_gemm_dev.cu)
 };
+#ifndef TC_VEC_STORE
+#define TC_VEC_STORE 0
+#endif
+#ifdef GSCAN_TC_TIMELINE
+#define TC_STAMP(role, idx) do { if (p.timeline && blockIdx.x == 0 && (idx) < 128) p.timeline[(role) * 128 + (idx)] = clock64(); } while (0)
+#else
+#define TC_STAMP(role, idx) do { } while (0)
+#endif
 // MN-major tf32 operands exist only in the 32-byte-atom flavour of the 128-byte swizzle (layout type 1, TMA
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4 k-rows of 128 B per swizzle atom, atoms SBO = 512 B apart.
-struct MnConfig { uint32_t layout = 1, sbo = 512, lbo = BK * 128; int tma_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; };
+struct MnConfig { uint32_t layout = 1, sbo = 512, lbo = BK * 128; int tma_swizzle = (int)CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; long long* timeline = nullptr; };
 inline MnConfig& mn_config() { static MnConfig c; return c; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,7 +142,82 @@ __host__ __device__ constexpr uint32_t make_idesc(bool a_mn, bool b_mn, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
+// hi part of the split.  Default: truncation, which is what the tensor core does by itself when it reads an fp32
+// word as tf32 - so the raw tile IS the hi operand and only lo = x - trunc(x) has to be written (measured:
+// 5e-6 worst error relative to the typical |sum| at K = 400, against 3e-6 for the round-to-nearest split, which
+// costs another 32 KB of shared-memory writes per K-block; -DGSCAN_TC_RN_SPLIT selects it).
+#ifdef GSCAN_TC_RN_SPLIT
+__device__ __forceinline__ uint32_t tf32_hi_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+#else
+__device__ __forceinline__ uint32_t tf32_hi_bits(float x) { return __float_as_uint(x) & 0xffffe000u; }
+#endif
 __device__ __forceinline__ uint32_t tf32_rn_bits(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+
+// One lane's column of a 32-row block: 8 independent shared loads, then 8 global stores (128 B per warp each).
+// MODE 0 store, 1 tanh, 2 relu, 3 accumulate onto C, 4 atomic add (split-K partial sums).
+template <int MODE>
+__device__ __forceinline__ void store_rows(float* dst, long ldc, const float* src, int rows, float bsum) {
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = src[(r0 + i) * 33] + bsum;
+    if (MODE == 3) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (r0 + i < rows) v[i] += dst[(long)(r0 + i) * ldc];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (r0 + i < rows) {
+        float* d = dst + (long)(r0 + i) * ldc;
+        if (MODE == 1) *d = act_tanh(v[i]);
+        else if (MODE == 2) *d = fmaxf(v[i], 0.f);
+        else if (MODE == 4) atomicAdd(d, v[i]);
+        else *d = v[i];
+      }
+    }
+  }
+}
+
+// Vector form: the warp covers 4 rows x 128 B per instruction (lane = row r0 + lane/8, 16-byte chunk lane%8);
+// `src` is the warp's transpose tile with a row pitch of 36 floats.  Needs 16-byte aligned rows of C.
+template <int MODE>
+__device__ __forceinline__ void store_rows_v4(float* dst, long ldc, const float* tile, int lane, int rows, int cols,
+                                              float4 bsum) {
+  const int rr = lane >> 3, cc = (lane & 7) * 4;
+  if (cc >= cols) return;
+#pragma unroll
+  for (int r0 = 0; r0 < 32; r0 += 16) {
+    float4 v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(tile + (r0 + 4 * i + rr) * 36 + cc);
+      v[i].x += bsum.x; v[i].y += bsum.y; v[i].z += bsum.z; v[i].w += bsum.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 4 * i + rr;
+      if (r < rows) {
+        float* d = dst + (long)r * ldc + cc;
+        if (MODE == 4) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v[i].x), "f"(v[i].y), "f"(v[i].z),
+                       "f"(v[i].w) : "memory");
+        } else {
+          if (MODE == 3) {
+            const float4 o = *reinterpret_cast<const float4*>(d);
+            v[i].x += o.x; v[i].y += o.y; v[i].z += o.z; v[i].w += o.w;
+          } else if (MODE == 1) {
+            v[i].x = act_tanh(v[i].x); v[i].y = act_tanh(v[i].y); v[i].z = act_tanh(v[i].z); v[i].w = act_tanh(v[i].w);
+          } else if (MODE == 2) {
+            v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f);
+          }
+          *reinterpret_cast<float4*>(d) = v[i];
+        }
+      }
+    }
+  }
+}
 
 template <bool AK, bool BKM>   // operand contiguous along K in global memory (else along M / N)
 __global__ void __launch_bounds__(THREADS, 1)
@@ -138,8 +232,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto full_cvt = [&](int s) { return bar0 + 8u * (STAGES + s); };
   auto empty = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
   auto acc_full = [&](int b) { return bar0 + 8u * (3 * STAGES + b); };
-  auto acc_empty = [&](int b) { return bar0 + 8u * (3 * STAGES + 2 + b); };
-  const uint32_t tmem_slot = bar0 + 8u * (3 * STAGES + 4);
+  auto acc_empty = [&](int b) { return bar0 + 8u * (3 * STAGES + ACC_BUFS + b); };
+  const uint32_t tmem_slot = bar0 + 8u * (3 * STAGES + 2 * ACC_BUFS);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -149,7 +243,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(full_cvt(s), CVT_THREADS);
       mbar_init(empty(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < ACC_BUFS; ++b) {
       mbar_init(acc_full(b), 1);
       mbar_init(acc_empty(b), EPI_THREADS);
     }
@@ -187,6 +281,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int it = 0; it < nkb; ++it, ++g) {
           const int s = g % STAGES;
           mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
+          TC_STAMP(0, g);
           const uint32_t st = base + s * STAGE_BYTES;
           const int k = (kb0 + it) * BK;
           mbar_arrive_expect_tx(full_raw(s), 2 * TILE_BYTES);
@@ -219,12 +314,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int in_win = 0;
         for (int it = 0; it < nkb; ++it, ++g) {
           const int s = g % STAGES;
-          const uint32_t tacc = tmem_base + (uint32_t)((w & 1) * BN);
-          if (in_win == 0) {   // the accumulate warps must have drained this TMEM buffer (two windows ago)
-            mbar_wait(acc_empty(w & 1), ((w >> 1) & 1) ^ 1);
+          const int ab = w % ACC_BUFS;
+          const uint32_t tacc = tmem_base + (uint32_t)(ab * BN);
+          if (in_win == 0) {   // the accumulate warps must have drained this TMEM buffer (ACC_BUFS windows ago)
+            mbar_wait(acc_empty(ab), ((w / ACC_BUFS) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           }
           mbar_wait(full_cvt(s), (g / STAGES) & 1);
+          TC_STAMP(1, g);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t st = base + s * STAGE_BYTES;
           const uint32_t a_hi = st, a_lo = st + TILE_BYTES, b_hi = st + 2 * TILE_BYTES, b_lo = st + 3 * TILE_BYTES;
@@ -243,7 +340,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mma_commit(empty(s));               // frees the stage once these MMAs have read it
           ++in_win;
           if (in_win == FLUSH || it == nkb - 1) {
-            mma_commit(acc_full(w & 1));      // window complete: hand the TMEM buffer to the accumulate warps
+            mma_commit(acc_full(ab));         // window complete: hand the TMEM buffer to the accumulate warps
             ++w;
             in_win = 0;
           }
@@ -260,6 +357,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int it = 0; it < nkb; ++it, ++g) {
         const int s = g % STAGES;
         mbar_wait(full_raw(s), (g / STAGES) & 1);
+        if (ct == 0) TC_STAMP(2, g);
         uint8_t* st = gen_base + (size_t)s * STAGE_BYTES;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {   // A then B
@@ -271,11 +369,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float4 h, l;
-            h.x = __uint_as_float(tf32_rn_bits(v[i].x)); l.x = __uint_as_float(tf32_rn_bits(v[i].x - h.x));
-            h.y = __uint_as_float(tf32_rn_bits(v[i].y)); l.y = __uint_as_float(tf32_rn_bits(v[i].y - h.y));
-            h.z = __uint_as_float(tf32_rn_bits(v[i].z)); l.z = __uint_as_float(tf32_rn_bits(v[i].z - h.z));
-            h.w = __uint_as_float(tf32_rn_bits(v[i].w)); l.w = __uint_as_float(tf32_rn_bits(v[i].w - h.w));
+            h.x = __uint_as_float(tf32_hi_bits(v[i].x)); l.x = __uint_as_float(tf32_rn_bits(v[i].x - h.x));
+            h.y = __uint_as_float(tf32_hi_bits(v[i].y)); l.y = __uint_as_float(tf32_rn_bits(v[i].y - h.y));
+            h.z = __uint_as_float(tf32_hi_bits(v[i].z)); l.z = __uint_as_float(tf32_rn_bits(v[i].z - h.z));
+            h.w = __uint_as_float(tf32_hi_bits(v[i].w)); l.w = __uint_as_float(tf32_rn_bits(v[i].w - h.w));
+#ifdef GSCAN_TC_RN_SPLIT
             hi[ct + i * CVT_THREADS] = h;
+#endif
             lo[ct + i * CVT_THREADS] = l;
           }
         }
@@ -289,7 +389,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // into its fp32 accumulator with truncation, so every FLUSH K-blocks the window sum is folded into registers
     // with round-to-nearest adds (same policy as sgemm_kernel).
     const int q = warp & 3;
-    float* stage_out = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES) + (warp - 6) * (32 * 33);
+    float* stage_out = reinterpret_cast<float*>(gen_base + STAGES * STAGE_BYTES) + (warp - 6) * (32 * 36);
     const bool split = p.ksplit > 1;
     int w = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -301,9 +401,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < BN; ++j) acc[j] = 0.f;
       for (int i = 0; i < nwin; ++i, ++w) {
-        mbar_wait(acc_full(w & 1), (w >> 1) & 1);
+        const int ab = w % ACC_BUFS;
+        mbar_wait(acc_full(ab), (w / ACC_BUFS) & 1);
+        if (threadIdx.x == 192) TC_STAMP(3, w);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)((w & 1) * BN);
+        const uint32_t tacc = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ab * BN);
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           if (c * 32 < n_valid) {            // warp-uniform
@@ -314,40 +416,63 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(acc_empty(w & 1));
+        mbar_arrive(acc_empty(ab));
       }
       // write-out: per-warp 32x32 transpose through shared memory so that every global access is a full 128-B row segment
+      const int mode = split ? 4 : (p.accumulate ? 3 : p.act);     // warp-uniform
+      const int rows = min(32, p.M - (m0 + 32 * q));
+      const bool vec = TC_VEC_STORE && ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      int tl_i = 5 * ((tile - blockIdx.x) / gridDim.x);
+      if (threadIdx.x == 192) TC_STAMP(4, tl_i);
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
-        if (c * 32 < n_valid) {
+        if (c * 32 < n_valid && rows > 0) {
           __syncwarp();
+          if (vec) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) stage_out[lane * 33 + j] = acc[c * 32 + j];
-          __syncwarp();
-          const int gn = n0 + c * 32 + lane;
-          float bsum = 0.f;
-          if (!split && gn < p.N) {
-            if (p.bias) bsum += __ldg(p.bias + gn);
-            if (p.bias2) bsum += __ldg(p.bias2 + gn);
-          }
-          if (gn < p.N) {
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-              const int gm = m0 + 32 * q + r;
-              if (gm >= p.M) break;
-              float val = stage_out[r * 33 + lane];
-              float* dst = p.C + (long)gm * p.ldc + gn;
-              if (split) {
-                atomicAdd(dst, val);
-              } else {
-                val += bsum;
-                if (p.act == 1) val = act_tanh(val);
-                else if (p.act == 2) val = fmaxf(val, 0.f);
-                if (p.accumulate) val += *dst;
-                *dst = val;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stage_out + lane * 36 + j) =
+                  make_float4(acc[c * 32 + j], acc[c * 32 + j + 1], acc[c * 32 + j + 2], acc[c * 32 + j + 3]);
+            __syncwarp();
+            const int gn = n0 + c * 32 + (lane & 7) * 4;
+            float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!split && gn < p.N) {
+              if (p.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gn)); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
+              if (p.bias2) { const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + gn)); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
+            }
+            float* dst = p.C + (long)(m0 + 32 * q) * p.ldc + n0 + c * 32;
+            const int cols = n_valid - c * 32;
+            switch (mode) {
+              case 0: store_rows_v4<0>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
+              case 1: store_rows_v4<1>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
+              case 2: store_rows_v4<2>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
+              case 3: store_rows_v4<3>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
+              default: store_rows_v4<4>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) stage_out[lane * 33 + j] = acc[c * 32 + j];
+            __syncwarp();
+            if (threadIdx.x == 192) TC_STAMP(4, 64 + tl_i + 1 + c);
+            const int gn = n0 + c * 32 + lane;
+            if (gn < p.N) {
+              float bsum = 0.f;
+              if (!split) {
+                if (p.bias) bsum += __ldg(p.bias + gn);
+                if (p.bias2) bsum += __ldg(p.bias2 + gn);
+              }
+              float* dst = p.C + (long)(m0 + 32 * q) * p.ldc + gn;
+              const float* src = stage_out + lane;
+              switch (mode) {
+                case 0: store_rows<0>(dst, p.ldc, src, rows, bsum); break;
+                case 1: store_rows<1>(dst, p.ldc, src, rows, bsum); break;
+                case 2: store_rows<2>(dst, p.ldc, src, rows, bsum); break;
+                case 3: store_rows<3>(dst, p.ldc, src, rows, bsum); break;
+                default: store_rows<4>(dst, p.ldc, src, rows, bsum); break;
               }
             }
           }
+          if (threadIdx.x == 192) TC_STAMP(4, tl_i + 1 + c);
         }
       }
     }
@@ -442,7 +567,7 @@ inline int launch(const float* A, long a_rs, long a_cs, const float* B, long b_r
   if (rc) return rc;
   rc = bk ? make_map(&tb, B, K, N, ldb, BN) : make_map(&tb, B, N, K, ldb, BK, mn_swz);
   if (rc) return rc;
-  Params p{C, ldc, M, N, K, bias, bias2, act, accumulate, 0, 0, 1, mc.layout, mc.sbo, mc.lbo};
+  Params p{C, ldc, M, N, K, bias, bias2, act, accumulate, 0, 0, 1, mc.layout, mc.sbo, mc.lbo, mc.timeline};
   p.kb_total = ceil_div(K, BK);
   if (ksplit < 1) ksplit = 1;
   p.kb_per = ceil_div(p.kb_total, ksplit);

@@ -262,12 +262,12 @@ int check_common(const gscan_dims* d, const float* const* params) {
 // NT product: C[M,N] = act(A[M,K] (lda) . W[N,K]^T (ldw) + bias + bias2)
 int linear(const float* A, long lda, const float* W, long ldw, float* C, long ldc, int M, int N, int K,
            const float* bias, const float* bias2, int act, cudaStream_t st) {
-  return launch_sgemm(A, lda, 1, W, 1, ldw, C, ldc, M, N, K, bias, bias2, act, 0, 1, st);
+  return launch_gemm(A, lda, 1, W, 1, ldw, C, ldc, M, N, K, bias, bias2, act, 0, 1, st);
 }
 // NN product: C[M,N] (+)= A[M,K] (lda) . W[K,N] (ldw)
 int matmul_nn(const float* A, long lda, const float* W, long ldw, float* C, long ldc, int M, int N, int K,
               int accumulate, cudaStream_t st) {
-  return launch_sgemm(A, lda, 1, W, ldw, 1, C, ldc, M, N, K, nullptr, nullptr, 0, accumulate, 1, st);
+  return launch_gemm(A, lda, 1, W, ldw, 1, C, ldc, M, N, K, nullptr, nullptr, 0, accumulate, 1, st);
 }
 
 int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* situations, const float* drop_cnn,
@@ -1163,8 +1163,21 @@ int gscan_sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int6
                 int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, int32_t act, int32_t accumulate,
                 void* stream) {
   if (!A || !B || !C || M < 0 || N < 0 || K < 0) return GSCAN_E_BADARG;
-  return launch_sgemm(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, bias, nullptr, act, accumulate, 1,
-                      (cudaStream_t)stream);
+  return launch_gemm(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, bias, nullptr, act, accumulate, 1,
+                     (cudaStream_t)stream);
+}
+
+int gscan_sgemm_path(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs, float* C,
+                     int64_t ldc, int32_t M, int32_t N, int32_t K, const float* bias, int32_t act, int32_t accumulate,
+                     int32_t ksplit, int32_t path, void* stream) {
+  if (!A || !B || !C || M < 0 || N < 0 || K < 0 || ksplit < 1 || (path != 0 && path != 1)) return GSCAN_E_BADARG;
+  if (ksplit > 1 && (bias || act)) return GSCAN_E_BADARG;
+  if (path == 0)
+    return launch_sgemm(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, bias, nullptr, act, accumulate, ksplit,
+                        (cudaStream_t)stream);
+  if (!tc::eligible(A, a_rs, a_cs, B, b_rs, b_cs, M, N, K)) return GSCAN_E_UNSUPPORTED;
+  return tc::launch(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, bias, nullptr, act, accumulate, ksplit,
+                    (cudaStream_t)stream);
 }
 
 int gscan_cnn_forward(const gscan_dims* d, const float* const* P, const float* situations, const float* drop_cnn,

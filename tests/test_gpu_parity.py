@@ -53,6 +53,68 @@ def test_sgemm_forms(M, N, K):
     assert (run(Ad, K, 1, Bd, N, 1, acc=1, C=C0) - (ref + 1)).abs().max() < tol
 
 
+@pytest.mark.parametrize("M,N,K,ksplit", [(24200, 100, 400, 1), (24200, 400, 100, 1), (200, 100, 100, 1),
+                                          (7200, 100, 152, 1), (400, 100, 24200, 37), (400, 200, 24200, 18),
+                                          (100, 100, 24200, 148), (300, 260, 1000, 1), (64, 32, 32, 1),
+                                          (129, 132, 40, 3)])
+def test_sgemm_tcgen05_path(M, N, K, ksplit):
+    """The tcgen05 / TMA GEMM (csrc/gemm_tc.cuh) in all four operand-major combinations, against fp64 and against
+    the mma.sync kernel.  Tolerance: 2e-5 of the typical |sum| (both kernels are 3xTF32; fp32 itself is ~1e-6)."""
+    lib = pkg.load()
+    g = torch.Generator().manual_seed(M + 7 * N + 13 * K)
+    A = torch.randn(M, K, generator=g, dtype=torch.float64)
+    Bm = 0.1 * torch.randn(K, N, generator=g, dtype=torch.float64)
+    bias = torch.randn(N, generator=g, dtype=torch.float64)
+    ref = A @ Bm
+    scale = (A.abs() @ Bm.abs()).max().item() / K ** 0.5
+    tol = 2e-5 * scale
+    st = torch.cuda.current_stream().cuda_stream
+    # leading dimensions padded to multiples of 4 floats (TMA needs 16-byte row strides)
+    Kp, Np, Mp = (K + 3) // 4 * 4, (N + 3) // 4 * 4, (M + 3) // 4 * 4
+    A_k = torch.zeros(M, Kp, device=DEV); A_k[:, :K] = A.float().to(DEV)          # A(i,k) K-contiguous
+    A_m = torch.zeros(K, Mp, device=DEV); A_m[:, :M] = A.t().float().to(DEV)      # A(i,k) M-contiguous
+    B_k = torch.zeros(N, Kp, device=DEV); B_k[:, :K] = Bm.t().float().to(DEV)     # B(k,j) K-contiguous
+    B_n = torch.zeros(K, Np, device=DEV); B_n[:, :N] = Bm.float().to(DEV)         # B(k,j) N-contiguous
+
+    def run(path, a, a_rs, a_cs, b, b_rs, b_cs, bias_t=None, act=0, acc=0, init=0.0, ks=ksplit):
+        C = torch.full((M, Np), init, device=DEV)
+        rc = lib.gscan_sgemm_path(a.data_ptr(), a_rs, a_cs, b.data_ptr(), b_rs, b_cs, C.data_ptr(), Np, M, N, K,
+                                  None if bias_t is None else bias_t.data_ptr(), act, acc, ks, path, st)
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        return C[:, :N].cpu().double()
+
+    forms = {"NT": (A_k, Kp, 1, B_k, 1, Kp), "NN": (A_k, Kp, 1, B_n, Np, 1),
+             "TN": (A_m, 1, Mp, B_n, Np, 1), "TT": (A_m, 1, Mp, B_k, 1, Kp)}
+    for name, f in forms.items():
+        out = run(1, *f)
+        assert (out - ref).abs().max() < tol, (name, (out - ref).abs().max().item(), tol)
+        old = run(0, *f)
+        assert (out - old).abs().max() < tol, name
+    if ksplit == 1:
+        bt = bias.float().to(DEV)
+        out = run(1, *forms["NT"], bias_t=bt, act=1)
+        assert (out - torch.tanh(ref + bias)).abs().max() < tol + 1e-6
+        out = run(1, *forms["NN"], bias_t=bt, act=2)
+        assert (out - torch.relu(ref + bias)).abs().max() < tol
+        out = run(1, *forms["NT"], acc=1, init=1.0)
+        assert (out - (ref + 1)).abs().max() < tol
+    else:   # split-K adds onto what C holds
+        out = run(1, *forms["TN"], init=2.0)
+        assert (out - (ref + 2)).abs().max() < tol
+
+
+def test_sgemm_tcgen05_rejects_unaligned():
+    lib = pkg.load()
+    st = torch.cuda.current_stream().cuda_stream
+    A = torch.zeros(256, 150, device=DEV)     # row stride 600 B: not a multiple of 16
+    Bm = torch.zeros(128, 150, device=DEV)
+    C = torch.zeros(256, 128, device=DEV)
+    rc = lib.gscan_sgemm_path(A.data_ptr(), 150, 1, Bm.data_ptr(), 1, 150, C.data_ptr(), 128, 256, 128, 150, None, 0, 0,
+                              1, 1, st)
+    assert rc == -2
+
+
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_encode_input_matches_golden(name):
     cfg, meta, params, batch, z = load_case(name, dtype=torch.float32)

@@ -95,6 +95,26 @@ int main(int argc, char** argv) {
     cudaEventRecord(e0, st);
     for (int r = 0; r < reps; ++r) launch_sgemm(dA, a_rs, a_cs, dB, b_rs, b_cs, dC2, c.ldc, c.M, c.N, c.K, nullptr, nullptr, 0, 0, c.ksplit, st);
     cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms_old, e0, e1);
+#ifdef GSCAN_TC_TIMELINE
+    {
+      long long* dtl; cudaMalloc(&dtl, 5 * 128 * 8); cudaMemset(dtl, 0, 5 * 128 * 8);
+      tc::mn_config().timeline = dtl;
+      tc::launch(dA, a_rs, a_cs, dB, b_rs, b_cs, dC, c.ldc, c.M, c.N, c.K, nullptr, nullptr, 0, 0, c.ksplit, st);
+      cudaStreamSynchronize(st);
+      tc::mn_config().timeline = nullptr;
+      std::vector<long long> tl(640);
+      cudaMemcpy(tl.data(), dtl, 640 * 8, cudaMemcpyDeviceToHost);
+      long long t0 = tl[0];
+      const char* names[5] = {"tma issue ", "mma start ", "cvt start ", "acc window", "write-out "};
+      for (int r = 0; r < 5; ++r) {
+        printf("  %s:", names[r]);
+        for (int i = 0; i < 28 && tl[r * 128 + i]; ++i) printf(" %lld", tl[r * 128 + i] - t0);
+        if (r == 4) { printf("\n   after STS:"); for (int i = 65; i < 65 + 20; ++i) printf(" %lld", tl[r * 128 + i] ? tl[r * 128 + i] - t0 : 0); }
+        printf("\n");
+      }
+      cudaFree(dtl);
+    }
+#endif
     printf("%s M=%d N=%d K=%d split=%d | tcgen05 err %.2e (mma.sync err %.2e) maxdiff %.2e scale %.2f | %.1f us vs %.1f us\n",
            c.name, c.M, c.N, c.K, c.ksplit, err, err2, maxdiff, scale, 1e3 * ms_tc / reps, 1e3 * ms_old / reps);
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dC2); cudaFree(dbias);
