@@ -60,6 +60,44 @@ void prof_mark(int idx, cudaStream_t st) {
   g_stage_seen[idx] = true;
 }
 
+// ---- internal fork / join ------------------------------------------------------------------
+// Independent chains of small kernels (CNN | command encoder | decoder prelude; after the reverse sweep:
+// decoder weight gradients | visual keys -> CNN | textual keys -> encoder) run on two helper streams that fork
+// from and join back into the caller's stream through events, so the caller still sees plain stream semantics:
+// everything a call enqueues completes before anything the caller enqueues on `stream` afterwards.
+struct SideStreams {
+  cudaStream_t s[2] = {nullptr, nullptr};
+  cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+SideStreams* side_streams() {
+  static SideStreams per_device[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStreams& S = per_device[dev];
+  if (!S.ok) {
+    for (int i = 0; i < 2; ++i) {
+      if (cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&S.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&S.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    S.ok = true;
+  }
+  return &S;
+}
+// side stream i starts after everything enqueued on `from` so far
+int fork_side(SideStreams* S, int i, cudaStream_t from) {
+  TRYCUDA(cudaEventRecord(S->fork_ev[i], from));
+  TRYCUDA(cudaStreamWaitEvent(S->s[i], S->fork_ev[i], 0));
+  return 0;
+}
+// `into` continues after everything enqueued on side stream i so far
+int join_side(SideStreams* S, int i, cudaStream_t into) {
+  TRYCUDA(cudaEventRecord(S->join_ev[i], S->s[i]));
+  TRYCUDA(cudaStreamWaitEvent(into, S->join_ev[i], 0));
+  return 0;
+}
+
 // ---- workspace layout --------------------------------------------------------------------
 struct Layout {
   size_t total = 0;
@@ -290,8 +328,12 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
                      const float* situations, const float* drop_cnn, const float* drop_enc, float* ws,
                      const Layout& L, bool need_keys, cudaStream_t st) {
   const int B = d.B, Ti = d.Ti, M = d.G * d.G, D = 3 * d.F, H = d.H, E = d.E;
-  TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, st));
-  if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, st));
+  // the situation CNN (+ visual keys) is independent of the command encoder: helper stream 0
+  SideStreams* S = side_streams();
+  cudaStream_t sc = S ? S->s[0] : st;
+  if (S) TRY(fork_side(S, 0, st));
+  TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, sc));
+  if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, sc));
   // command embeddings and their input-gate pre-activations for both directions
   {
     long n = (long)B * Ti * E;
@@ -329,6 +371,7 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
     TRY(linear(ws + L.enc_out, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.KT, H, Ti * B, H, H, nullptr, nullptr, 0, st));
     TRY(linear(ws + L.h_enc, H, P[GSCAN_P_E2D_W], H, ws + L.h0, H, B, H, H, P[GSCAN_P_E2D_B], nullptr, 1, st));
   }
+  if (S) TRY(join_side(S, 0, st));
   return 0;
 }
 
@@ -739,20 +782,25 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   const long long* tgts = reinterpret_cast<const long long*>(targets);
 
   prof_mark(0, st);
-  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, st));
-  prof_mark(1, st);
-  TRY(pack_decoder_weights(*d, P, ws, L, st));
+  // decoder prelude (depends on targets and weights only) on helper stream 1, beside the encoder side
+  SideStreams* S = side_streams();
+  cudaStream_t sp = S ? S->s[1] : st;
+  if (S) TRY(fork_side(S, 1, st));
+  TRY(pack_decoder_weights(*d, P, ws, L, sp));
   // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
   {
     long n = (long)B * Tt * H;
-    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sp>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
                                                               4 * H, B, Tt, 1);
     GSCAN_CHECK_LAUNCH();
   }
   float* U1 = ws + L.U + (size_t)B * 4 * H;
   // input-gate pre-activations of every step at once: Xe = E . W_ih[:, :H]^T + b_ih + b_hh
   TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, Tt * B, 4 * H, H, P[GSCAN_P_DEC_BIH],
-             P[GSCAN_P_DEC_BHH], 0, st));
+             P[GSCAN_P_DEC_BHH], 0, sp));
+  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, st));
+  prof_mark(1, st);
+  if (S) TRY(join_side(S, 1, st));
   DecFwdP p{};
   fill_dec_fwd_common(*d, P, ws, L, p);
   p.T = Tt;
@@ -839,7 +887,10 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, st));
   // B2: output_to_hidden
   TRY(matmul_nn(ws + L.dpre, H, P[GSCAN_P_O2H_W], 4 * H, ws + L.dU, 4 * H, R, 4 * H, H, 0, st));
+  // (kept on the caller's stream: a persistent GEMM on a helper stream here delays the cluster launch of the
+  // sweep behind it - measured 1.11 -> 1.45 ms for the sweep)
   TRY(launch_grad_gemm(ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H, R, sms, st));
+  SideStreams* S = side_streams();
   // B3: auxiliary head
   const float* dbeta_aux = nullptr;
   if (d->auxiliary_task && d_aux_logp) {
@@ -877,21 +928,32 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     if (rc == 0) bwd_v3 = true;
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
   }
+  // Three independent chains from here, joined before returning:
+  //   caller's stream  decoder weight gradients, decoder embedding
+  //   helper stream 0  value path of both attentions (dc_T, dc_V -> dK^V, dK^T), then visual keys -> CNN
+  //   helper stream 1  (after the value path) textual keys -> initial state -> command encoder
+  cudaStream_t sv = S ? S->s[0] : st, stx = S ? S->s[1] : st;
   if (bwd_v3) {
     prof_mark(7, st);   // the sweep kernel alone; what follows counts as batched weight-gradient work
+    if (S) TRY(fork_side(S, 0, st));
     // value path of both attentions, outside the recurrence: dc_T, dc_V for all steps as batched products,
     // accumulated into the (already consumed) [c_T | c_V] columns of dU, then dK += sum_t w_t dc_t
-    TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH] + H, 3 * H, ws + L.dU + 2 * H, 4 * H, R, 2 * H, 4 * H, 1, st));
+    TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH] + H, 3 * H, ws + L.dU + 2 * H, 4 * H, R, 2 * H, 4 * H, 1, sv));
     if (d->conditional_attention)
-      TRY(matmul_nn(ws + L.dd, H, P[GSCAN_P_COND_W] + H, 2 * H, ws + L.dU + 2 * H, 4 * H, R, H, H, 1, st));
+      TRY(matmul_nn(ws + L.dd, H, P[GSCAN_P_COND_W] + H, 2 * H, ws + L.dU + 2 * H, 4 * H, R, H, H, 1, sv));
     size_t smem = sizeof(float) * (size_t)Tt * ((((M > Ti ? M : Ti) + 3) & ~3) + H);
     if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_bwd_kernel, smem));
-    v3::attn_value_bwd_kernel<<<dim3(B, 2), 256, smem, st>>>(ws + L.dU + 2 * H, 4 * H, ws + L.beta, ws + L.alpha, B, Tt, Ti,
+    v3::attn_value_bwd_kernel<<<dim3(B, 2), 256, smem, sv>>>(ws + L.dU + 2 * H, 4 * H, ws + L.beta, ws + L.alpha, B, Tt, Ti,
                                                              M, H, ws + L.dKV, ws + L.dKT);
     GSCAN_CHECK_LAUNCH();
+    if (S) TRY(fork_side(S, 1, sv));   // helper stream 1 continues after the value path
   } else {
     TRY(launch_dec_bwd(*d, bp, st));
     prof_mark(7, st);
+    if (S) {
+      TRY(fork_side(S, 0, st));
+      TRY(fork_side(S, 1, st));
+    }
   }
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
@@ -919,34 +981,34 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
         tgts, Tt, ws + L.dU, 4 * H, drop_dec, G[GSCAN_P_DEC_EMB], H, V, d->pad_idx_out, B, Tt, 1, rpb, use_smem);
     GSCAN_CHECK_LAUNCH();
   }
-  // B6: visual keys -> CNN
   prof_mark(8, st);
-  TRY(launch_grad_gemm(ws + L.dKV, H, ws + L.feat, D, G[GSCAN_P_VIS_KEY_W], D, H, D, B * M, sms, st));
-  TRY(matmul_nn(ws + L.dKV, H, P[GSCAN_P_VIS_KEY_W], D, ws + L.dfeat, D, B * M, D, H, 0, st));
+  // B6: visual keys -> CNN (helper stream 0)
+  TRY(launch_grad_gemm(ws + L.dKV, H, ws + L.feat, D, G[GSCAN_P_VIS_KEY_W], D, H, D, B * M, sms, sv));
+  TRY(matmul_nn(ws + L.dKV, H, P[GSCAN_P_VIS_KEY_W], D, ws + L.dfeat, D, B * M, D, H, 0, sv));
   {
     long n = (long)B * M * D;
-    cnn_dact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ws + L.dfeat, ws + L.feat, drop_cnn, ws + L.dconv, n);
+    cnn_dact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sv>>>(ws + L.dfeat, ws + L.feat, drop_cnn, ws + L.dconv, n);
     GSCAN_CHECK_LAUNCH();
     CnnShape cs{B, d->G, d->C, d->F, d->K3};
-    TRYCUDA(cudaMemsetAsync(ws + L.dWt_cnn, 0, sizeof(float) * cs.wtotal(), st));
+    TRYCUDA(cudaMemsetAsync(ws + L.dWt_cnn, 0, sizeof(float) * cs.wtotal(), sv));
     size_t smem = (size_t)B * 8;
     if (smem > 48 * 1024) TRY(set_smem(cnn_wgrad_kernel, smem));
-    cnn_wgrad_kernel<<<M * d->C, 256, smem, st>>>(cs, situations, ws + L.dconv, ws + L.dWt_cnn);
+    cnn_wgrad_kernel<<<M * d->C, 256, smem, sv>>>(cs, situations, ws + L.dconv, ws + L.dWt_cnn);
     GSCAN_CHECK_LAUNCH();
-    cnn_relayout_kernel<<<ceil_div(cs.wtotal(), 256), 256, 0, st>>>(cs, G[GSCAN_P_CONV1_W], G[GSCAN_P_CONV2_W],
+    cnn_relayout_kernel<<<ceil_div(cs.wtotal(), 256), 256, 0, sv>>>(cs, G[GSCAN_P_CONV1_W], G[GSCAN_P_CONV2_W],
                                                                    G[GSCAN_P_CONV3_W], ws + L.dWt_cnn, 0);
     GSCAN_CHECK_LAUNCH();
-    TRY(launch_colsum(ws + L.dconv, D, B * M, d->F, G[GSCAN_P_CONV1_B], st));
-    TRY(launch_colsum(ws + L.dconv + d->F, D, B * M, d->F, G[GSCAN_P_CONV2_B], st));
-    TRY(launch_colsum(ws + L.dconv + 2 * d->F, D, B * M, d->F, G[GSCAN_P_CONV3_B], st));
+    TRY(launch_colsum(ws + L.dconv, D, B * M, d->F, G[GSCAN_P_CONV1_B], sv));
+    TRY(launch_colsum(ws + L.dconv + d->F, D, B * M, d->F, G[GSCAN_P_CONV2_B], sv));
+    TRY(launch_colsum(ws + L.dconv + 2 * d->F, D, B * M, d->F, G[GSCAN_P_CONV3_B], sv));
   }
-  // B7: textual keys and initial state
-  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, st));
-  TRY(matmul_nn(ws + L.dKT, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.denc_out, H, Ti * B, H, H, 0, st));
-  TRY(launch_tanh_bwd(ws + L.dh0, ws + L.h0, ws + L.dpre0, (long)B * H, st));
-  TRY(launch_grad_gemm(ws + L.dpre0, H, ws + L.h_enc, H, G[GSCAN_P_E2D_W], H, H, H, B, sms, st));
-  TRY(launch_colsum(ws + L.dpre0, H, B, H, G[GSCAN_P_E2D_B], st));
-  TRY(matmul_nn(ws + L.dpre0, H, P[GSCAN_P_E2D_W], H, ws + L.dh_enc, H, B, H, H, 0, st));
+  // B7: textual keys and initial state (helper stream 1)
+  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, stx));
+  TRY(matmul_nn(ws + L.dKT, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.denc_out, H, Ti * B, H, H, 0, stx));
+  TRY(launch_tanh_bwd(ws + L.dh0, ws + L.h0, ws + L.dpre0, (long)B * H, stx));
+  TRY(launch_grad_gemm(ws + L.dpre0, H, ws + L.h_enc, H, G[GSCAN_P_E2D_W], H, H, H, B, sms, stx));
+  TRY(launch_colsum(ws + L.dpre0, H, B, H, G[GSCAN_P_E2D_B], stx));
+  TRY(matmul_nn(ws + L.dpre0, H, P[GSCAN_P_E2D_W], H, ws + L.dh_enc, H, B, H, H, 0, stx));
   // B8: encoder BPTT
   EncP ep{};
   ep.B = B; ep.Ti = Ti; ep.H = H;
@@ -961,25 +1023,29 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   ep.len = cmd_len;
   ep.denc_out = ws + L.denc_out;
   ep.dh_enc = ws + L.dh_enc;
-  TRY(launch_enc(*d, ep, true, st));
+  TRY(launch_enc(*d, ep, true, stx));
   const int RE = B * Ti;
   const int wih[2] = {GSCAN_P_ENC_WIH, GSCAN_P_ENC_WIH_R}, whh[2] = {GSCAN_P_ENC_WHH, GSCAN_P_ENC_WHH_R};
   const int bih[2] = {GSCAN_P_ENC_BIH, GSCAN_P_ENC_BIH_R}, bhh[2] = {GSCAN_P_ENC_BHH, GSCAN_P_ENC_BHH_R};
   for (int i = 0; i < 2; ++i) {
-    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.enc_x, E, G[wih[i]], E, 4 * H, E, RE, sms, st));
-    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.hprev[i], H, G[whh[i]], H, 4 * H, H, RE, sms, st));
-    TRY(launch_colsum(ws + L.dga[i], 4 * H, RE, 4 * H, G[bih[i]], st));
-    TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
-    TRY(matmul_nn(ws + L.dga[i], 4 * H, P[wih[i]], E, ws + L.denc_x, E, RE, E, 4 * H, i, st));
+    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.enc_x, E, G[wih[i]], E, 4 * H, E, RE, sms, stx));
+    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.hprev[i], H, G[whh[i]], H, 4 * H, H, RE, sms, stx));
+    TRY(launch_colsum(ws + L.dga[i], 4 * H, RE, 4 * H, G[bih[i]], stx));
+    TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, stx));
+    TRY(matmul_nn(ws + L.dga[i], 4 * H, P[wih[i]], E, ws + L.denc_x, E, RE, E, 4 * H, i, stx));
   }
   {
-    TRYCUDA(cudaMemsetAsync(G[GSCAN_P_ENC_EMB], 0, sizeof(float) * (size_t)d->Vi * E, st));
+    TRYCUDA(cudaMemsetAsync(G[GSCAN_P_ENC_EMB], 0, sizeof(float) * (size_t)d->Vi * E, stx));
     int use_smem = ((size_t)d->Vi * E * sizeof(float) <= 48 * 1024);
     int rpb = 64;
-    embed_bwd_kernel<<<ceil_div(RE, rpb), 256, use_smem ? (size_t)d->Vi * E * sizeof(float) : 0, st>>>(
+    embed_bwd_kernel<<<ceil_div(RE, rpb), 256, use_smem ? (size_t)d->Vi * E * sizeof(float) : 0, stx>>>(
         cmds, d->Ti_stride, ws + L.denc_x, E, drop_enc, G[GSCAN_P_ENC_EMB], E, d->Vi, d->pad_idx_in, B, Ti, 0, rpb,
         use_smem);
     GSCAN_CHECK_LAUNCH();
+  }
+  if (S) {
+    TRY(join_side(S, 0, st));
+    TRY(join_side(S, 1, st));
   }
   prof_mark(9, st);
   return GSCAN_OK;
