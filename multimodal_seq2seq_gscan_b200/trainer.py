@@ -76,15 +76,16 @@ class FusedTrainer:
         Returns the (global-batch) loss share of this rank as a 0-dim device tensor - no host sync."""
         model = self.model
         model.train()
+        counts = work = None
+        if self.distributed:   # depends on the targets only: in flight during the forward pass
+            counts, work = dp.start_count_allreduce(targets, model.target_pad_idx, self.group)
         logp, aux = model(commands_input=commands, commands_lengths=commands_lengths, situations_input=situations,
                           target_batch=targets, target_lengths=target_lengths)
         nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1)
         aux_mean = None
         if model.auxiliary_task and target_positions is not None and self.weight_target_loss != 0:
             aux_mean = model.get_auxiliary_loss(aux, target_positions)
-        counts = None
-        if self.distributed:
-            counts, work = dp.start_count_allreduce(n_tok, targets.shape[0], self.group)
+        if work is not None:
             work.wait()
         loss = dp.global_loss(nll, n_tok, aux_mean, targets.shape[0], self.weight_target_loss, counts)
         grads = torch.autograd.grad(loss, self._present)
