@@ -83,20 +83,28 @@ __global__ void __launch_bounds__(256) cnn_forward_kernel(CnnShape s, const floa
   compact_nonzero(x + (long)b * MC, 1, MC, idx_s, val_s, &count_s);
   __syncthreads();
   const int nnz = count_s;
+  // decode each non-zero once into (row | col << 8 | channel << 16): no integer division in the tap loop
+  for (int z = threadIdx.x; z < nnz; z += blockDim.x) {
+    const int e = idx_s[z];
+    const int ci_cell = e / s.C, ch = e - ci_cell * s.C;
+    const int ri = ci_cell / s.G, ci = ci_cell - ri * s.G;
+    idx_s[z] = ri | (ci << 8) | (ch << 16);
+  }
+  __syncthreads();
+  const int CF = s.C * s.F;
   for (int o = threadIdx.x; o < M * D; o += blockDim.x) {
-    int cell = o / D, n = o - cell * D;
-    int conv = n / s.F, f = n - conv * s.F;
-    int k = s.ksize(conv), p = k >> 1;
-    int ro = cell / s.G, co = cell - ro * s.G;
+    const int cell = o / D, n = o - cell * D;
+    const int conv = n / s.F, f = n - conv * s.F;
+    const int k = s.ksize(conv), p = k >> 1;
+    const int ro = cell / s.G, co = cell - ro * s.G;
     const float* w = Wt + s.woff(conv) + f;
     float acc = __ldg((conv == 0 ? b1 : (conv == 1 ? b2 : b3)) + f);
+    const int rbase = p - ro, cbase = p - co;
     for (int z = 0; z < nnz; ++z) {
-      int e = idx_s[z];
-      int ci_cell = e / s.C, ch = e - ci_cell * s.C;
-      int ri = ci_cell / s.G, ci = ci_cell - ri * s.G;
-      int dr = ri - ro + p, dc = ci - co + p;
-      if (dr >= 0 && dr < k && dc >= 0 && dc < k)
-        acc = fmaf(val_s[z], __ldg(w + (long)((dr * k + dc) * s.C + ch) * s.F), acc);
+      const int e = idx_s[z];
+      const int dr = (e & 255) + rbase, dc = ((e >> 8) & 255) + cbase;
+      if ((unsigned)dr < (unsigned)k && (unsigned)dc < (unsigned)k)
+        acc = fmaf(val_s[z], __ldg(w + (dr * k + dc) * CF + (e >> 16) * s.F), acc);
     }
     acc = fmaxf(acc, 0.f);
     long oi = (long)b * M * D + o;
