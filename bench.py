@@ -44,7 +44,16 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "compositional_splits: G=6 C=16 F=50 k3=7 E=25 H=100 Vi=21 V=9 B=200/GPU Ti=10 Tt=121 (all padded steps), no aux, dropout .3/.3/.1"
+WORKLOADS = {
+    # BASELINE.json configs[1] - the configuration the metric is quoted on (default)
+    "comp": "compositional_splits: G=6 C=16 F=50 k3=7 E=25 H=100 Vi=21 V=9 B=200/GPU Ti=10 Tt=121 (all padded steps), no aux, dropout .3/.3/.1",
+    # configs[2]: same with the auxiliary target-position task (weight 0.3)
+    "comp_aux": "compositional_splits + auxiliary target-position task (weight_target_loss 0.3): G=6 C=16 F=50 k3=7 E=25 H=100 Vi=21 V=9 B=200/GPU Ti=10 Tt=121, dropout .3/.3/.1",
+    # configs[4]: target_length_split shape (long action sequences, 13x13 third convolution)
+    "tlen": "target_length_split: G=6 C=16 F=50 k3=13 E=25 H=100 Vi=17 V=8 B=200/GPU Ti=10 Tt=121 (target lengths 17..121), no aux, dropout .3/.3/.1",
+}
+WORKLOAD = WORKLOADS["comp"]
+_WORKLOAD_KEY = "comp"
 SEED = 1234
 B_PER_GPU = 200
 # algorithmic FLOPs (2 per MAC) per example per decoder step inside the recurrent sweeps:
@@ -58,8 +67,9 @@ STEP_FLOP_PER_EXAMPLE = 206.5e6
 
 def bench_cfg():
     from multimodal_seq2seq_gscan_b200 import synthetic
-    cfg = dict(synthetic.CONFIGS["comp"])
-    cfg.update(encoder_dropout_p=0.3, decoder_dropout_p=0.3, cnn_dropout_p=0.1, auxiliary_task=False)
+    cfg = dict(synthetic.CONFIGS["tlen" if _WORKLOAD_KEY == "tlen" else "comp"])
+    cfg.update(encoder_dropout_p=0.3, decoder_dropout_p=0.3, cnn_dropout_p=0.1,
+               auxiliary_task=(_WORKLOAD_KEY == "comp_aux"))
     return cfg
 
 
@@ -136,7 +146,8 @@ class ClockSampler:
 
 def make_host_batch(cfg, seed):
     from multimodal_seq2seq_gscan_b200 import synthetic
-    return synthetic.synthetic_batch(cfg, batch_size=B_PER_GPU, seed=seed)
+    return synthetic.synthetic_batch(cfg, batch_size=B_PER_GPU, seed=seed,
+                                     min_tgt_len=17 if _WORKLOAD_KEY == "tlen" else 3)
 
 
 # --------------------------------------------------------------------------------------------
@@ -164,9 +175,11 @@ def cpu_reference_steps(cfg, steps, warmup, threads=None):
         t0 = time.perf_counter()
         drop = {"cnn": mask((B, M, D), cfg["cnn_dropout_p"]), "enc": mask((B, Ti, E), cfg["encoder_dropout_p"]),
                 "dec": mask((B, Tt, H), cfg["decoder_dropout_p"])}
-        logp, _ = O.model_forward(params, commands, batch["cmd_lengths"], situations, targets,
-                                  cfg["conditional_attention"], False, dropout=drop)
+        logp, aux = O.model_forward(params, commands, batch["cmd_lengths"], situations, targets,
+                                    cfg["conditional_attention"], cfg["auxiliary_task"], dropout=drop)
         loss = O.nll_loss(logp, targets)
+        if cfg["auxiliary_task"]:
+            loss = loss + 0.3 * O.aux_nll_loss(aux, torch.tensor(batch["target_positions"]))
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -218,9 +231,13 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="comp", choices=sorted(WORKLOADS),
+                    help="comp = BASELINE.json configs[1] (the headline); comp_aux / tlen = configs[2] / configs[4]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
+    global WORKLOAD, _WORKLOAD_KEY
+    _WORKLOAD_KEY, WORKLOAD = args.workload, WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference_arm(args, json_out)
         return
@@ -252,10 +269,12 @@ def main():
               for k in ("commands", "situations", "targets")}
     resident = {k: v.to(dev) for k, v in pinned.items()}
     cmd_len, tgt_len = host["cmd_lengths"], host["tgt_lengths"]
+    positions = torch.from_numpy(host["target_positions"]).to(dev) if cfg["auxiliary_task"] else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def step_resident():
-        return trainer.train_step(resident["commands"], cmd_len, resident["situations"], resident["targets"], tgt_len)
+        return trainer.train_step(resident["commands"], cmd_len, resident["situations"], resident["targets"], tgt_len,
+                                  positions)
 
     def barrier():
         if distributed:
@@ -304,7 +323,7 @@ def main():
             c = pinned["commands"].to(dev, non_blocking=True)
             s = pinned["situations"].to(dev, non_blocking=True)
             t = pinned["targets"].to(dev, non_blocking=True)
-            loss = trainer.train_step(c, cmd_len, s, t, tgt_len)
+            loss = trainer.train_step(c, cmd_len, s, t, tgt_len, positions)
             loss_pin[i % 2].copy_(loss, non_blocking=True)
             loss_ev[i % 2].record()
             if i > 0:
