@@ -197,6 +197,48 @@ def test_greedy_decode_matches_reference_predict(name):
     assert out2["tokens"].cpu().numpy().tolist() == z["greedy_noeos_sequences"].tolist()
 
 
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_batched_predict_and_evaluate_match_reference(name):
+    """predict() / evaluate() of the package over ragged batches give, per example, what the reference's
+    batch-1 predict() / evaluate() gave for the golden case (sequences, accuracies, exact match, aux accuracy)."""
+    from multimodal_seq2seq_gscan_b200 import predict as P
+    cfg, meta, params, batch, z = load_case(name, dtype=torch.float32)
+    model = build_model(cfg, params, train=False)
+    d = to_dev(batch)
+    N = int(z["greedy_max_steps"])
+    B = d["commands"].shape[0]
+    cuts = [0, max(1, B // 3), B]
+
+    def iterator():
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            Ti = int(batch["cmd_lengths"][lo:hi].max())
+            Tt = int(batch["tgt_lengths"][lo:hi].max())
+            yield (d["commands"][lo:hi, :Ti], batch["cmd_lengths"][lo:hi], [f"deriv{b}" for b in range(lo, hi)],
+                   d["situations"][lo:hi], [{"id": b} for b in range(lo, hi)], d["targets"][lo:hi, :Tt],
+                   batch["tgt_lengths"][lo:hi], torch.zeros(hi - lo, dtype=torch.long, device=DEV),
+                   torch.tensor(batch["target_positions"][lo:hi], device=DEV))
+
+    recs = list(P.predict(iterator(), model, N, 0, 1, 2))
+    assert len(recs) == B
+    for b, (inp, deriv, sit, out, tgt, att_c, att_s, aux) in enumerate(recs):
+        n = int(z["greedy_lengths"][b])
+        assert out == z["greedy_sequences"][b, :n].tolist()
+        assert deriv == [f"deriv{b}"] and sit == [{"id": b}]
+        assert inp.shape == (1, int(batch["cmd_lengths"][b])) and tgt.shape == (1, int(batch["tgt_lengths"][b]))
+        assert P.sequence_accuracy(out, tgt[0].tolist()[1:-1]) == pytest.approx(float(z["greedy_accuracy"][b]))
+        assert len(att_c) == n and len(att_s) == n
+        if n:
+            assert len(att_c[0][0]) == int(batch["cmd_lengths"][b]) and len(att_s[0][0]) == cfg["grid_size"] ** 2
+            np.testing.assert_allclose(np.sum(att_c[0][0]), 1.0, atol=1e-5)
+        if cfg["auxiliary_task"]:
+            assert aux == float(z["greedy_aux_accuracy"][b])
+    acc, em, aux_acc = P.evaluate(iterator(), model, N, 0, 1, 2)
+    assert acc == pytest.approx(float(np.mean(z["greedy_accuracy"])))
+    assert em == pytest.approx(100.0 * float(np.mean(z["greedy_accuracy"] == 100)))
+    if cfg["auxiliary_task"]:
+        assert aux_acc == pytest.approx(float(np.mean(z["greedy_aux_accuracy"])))
+
+
 @pytest.mark.parametrize("name", ["tiny_aux", "demo", "comp_small"])
 def test_decode_input_step_api(name):
     """predict.py's calling sequence: encode_input, key_layer x2, initialize_hidden, decode_input loop."""
