@@ -426,7 +426,6 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       if (!GREEDY && n < nb && h >= S0 && h < S0 + kHS) p.U[(size_t)(b0 + n) * H4 + kH + h] = hv;   // row group 0: h_{-1}
     }
     for (int i = tid; i < kNB * kGS; i += kThreads) g_s[i] = 0.f;
-    for (int i = tid; i < kNB * kM; i += kThreads) be_s[i] = 0.f;
     if (tid < kHS) {
       vT_s[tid] = __ldg(p.vT + S0 + tid);
       vV_s[tid] = __ldg(p.vV + S0 + tid);
@@ -464,7 +463,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     }
   }
   int my_len = 0, my_steps = 0;   // greedy bookkeeping of thread n < kNB
-  // be_s accumulates sum over steps of beta[n][m] (auxiliary head), written by the hq == 0 groups of the c_V phase
+  float bs0 = 0.f, bs1 = 0.f;   // sum over steps of beta[warp][lane], beta[warp][lane + 32]
   // Xe prefetch for the gate outputs this lane owns after its stage-A tile: rows lr0, lr0+8 x examples nF, nF+1
   const bool gate0 = roleA && lr0 >= 2 * kHS && lr0 < 6 * kHS, gate1 = roleA && lr0 + 8 >= 2 * kHS && lr0 + 8 < 6 * kHS;
   const int xe_col0 = gate0 ? ((lr0 - 2 * kHS) / kHS) * kH + S0 + (lr0 % kHS) : 0;
@@ -534,52 +533,38 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(3);
     mbar_wait(bar0 + 8u * 0, par);
     GSCAN3_STAMP(4);
+    if (warp < kNB) {
+      const int n = warp;
+      float s = -INFINITY;
+      if (lane < Ti) {
+        s = 0.f;
+#pragma unroll
+        for (int r = 0; r < kC; ++r) s += xT_s[(r * kNB + n) * Ti + lane];
+        if (lane >= len_s[n]) s = -INFINITY;
+      }
+      const float mx = warp_max(s);
+      const float e = (lane < Ti) ? __expf(s - mx) : 0.f;
+      const float sum = warp_sum(e);
+      const float a = e * (1.0f / sum);
+      if (lane < Ti) {
+        al_s[n * Ti + lane] = a;
+        if (!GREEDY && n < nb && rank == n % kC) p.alpha[(row0 + n) * Ti + lane] = a;
+        if (GREEDY && p.g_alphas && n < nb && rank == n % kC && alive_s[n])
+          p.g_alphas[((size_t)(b0 + n) * p.T + t) * Ti + lane] = a;
+      }
+    }
+    __syncthreads();
     GSCAN3_STAMP(5);
-    // ---- text softmax + everything linear in c_T through P_j = W K^T_j: q' slice (X3), gate contributions, c_T slice ----
-    // Every thread of an example recomputes the softmax of the summed partial scores (Ti <= 16 terms, the reads are
-    // warp broadcasts): no separate softmax phase, no block barrier.  Two passes (max, then exp / sum / weighted
-    // sum) so that no alpha array has to live in registers; the result is normalised at the end.
+    // ---- everything linear in c_T through P_j = W K^T_j: q' slice (X3), gate contributions, c_T slice ----
     if (tid < kNB * (QB + 5)) {
       const int n = tid / (QB + 5), q = tid - n * (QB + 5);
-      const int len = min(len_s[n], Ti);
-      const float* xs = xT_s + n * Ti;
-      float mx = -INFINITY;
-      for (int j = 0; j < len; ++j) {
-        float sc = 0.f;
-#pragma unroll
-        for (int r = 0; r < kC; ++r) sc += xs[r * kNB * Ti + j];
-        mx = fmaxf(mx, sc);
-      }
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-      float esum = 0.f;
       const float* src = (q < QB) ? P_s + (size_t)n * Ti * RBl + 4 * q : KT_s + (size_t)n * Ti * kHS + 4 * (q - QB);
       const int stride = (q < QB) ? RBl : kHS;
-      for (int j = 0; j < len; ++j) {
-        float sc = 0.f;
-#pragma unroll
-        for (int r = 0; r < kC; ++r) sc += xs[r * kNB * Ti + j];
-        const float e = __expf(sc - mx);
-        esum += e;
+      for (int j = 0; j < Ti; ++j) {
+        const float a = al_s[n * Ti + j];
         const float4 v = lds4(src + j * stride);
-        o.x = fmaf(e, v.x, o.x); o.y = fmaf(e, v.y, o.y); o.z = fmaf(e, v.z, o.z); o.w = fmaf(e, v.w, o.w);
-      }
-      const float inv = 1.0f / esum;
-      o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
-      if (q == 0 && n < nb && rank == n % kC) {   // one thread per example saves the weights (pads: 0)
-        float* ga = GREEDY ? (p.g_alphas && alive_s[n] ? p.g_alphas + ((size_t)(b0 + n) * p.T + t) * Ti : nullptr)
-                           : p.alpha + (row0 + n) * Ti;
-        if (ga) {
-          for (int j = 0; j < Ti; ++j) {
-            float a = 0.f;
-            if (j < len) {
-              float sc = 0.f;
-#pragma unroll
-              for (int r = 0; r < kC; ++r) sc += xs[r * kNB * Ti + j];
-              a = __expf(sc - mx) * inv;
-            }
-            ga[j] = a;
-          }
-        }
+        o.x = fmaf(a, v.x, o.x); o.y = fmaf(a, v.y, o.y); o.z = fmaf(a, v.z, o.z); o.w = fmaf(a, v.w, o.w);
       }
       if (COND && q < 5) {
         const float4 chv = lds4(ch_s + n * kHS + 4 * q);
@@ -629,62 +614,57 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(9);
     mbar_wait(bar0 + 8u * 2, par);
     GSCAN3_STAMP(10);
+    if (warp < kNB) {
+      const int n = warp;
+      float s0 = 0.f, s1 = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < kC; ++r) s0 += xV_s[(r * kNB + n) * kM + lane];
+      if (lane < kM - 32) {
+        s1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < kC; ++r) s1 += xV_s[(r * kNB + n) * kM + 32 + lane];
+      }
+      const float mx = warp_max(fmaxf(s0, s1));
+      const float e0 = __expf(s0 - mx), e1 = (lane < kM - 32) ? __expf(s1 - mx) : 0.f;
+      const float inv = 1.0f / warp_sum(e0 + e1);
+      const float w0 = e0 * inv, w1 = e1 * inv;
+      const bool counted = !GREEDY || alive_s[n] != 0;   // predict.py sums beta over generated steps only
+      be_s[n * kM + lane] = w0;
+      if (counted) bs0 += w0;
+      if (lane < kM - 32) {
+        be_s[n * kM + 32 + lane] = w1;
+        if (counted) bs1 += w1;
+      }
+      if (!GREEDY && n < nb && rank == n % kC) {
+        p.beta[(row0 + n) * kM + lane] = w0;
+        if (lane < kM - 32) p.beta[(row0 + n) * kM + 32 + lane] = w1;
+      }
+      if (GREEDY && p.g_betas && n < nb && rank == n % kC && counted) {
+        float* gb = p.g_betas + ((size_t)(b0 + n) * p.T + t) * kM;
+        gb[lane] = w0;
+        if (lane < kM - 32) gb[32 + lane] = w1;
+      }
+    }
+    __syncthreads();
     if (tid < kNB * 5 * 4) {
-      // visual softmax + c_V slice: 4 lanes per (example, hidden quad); lane u owns the 9 cells 4*mm + u.  Each 4-lane
-      // group recomputes the softmax of the example's 36 summed partial scores (max and sum by butterflies inside the
-      // group), so there is no separate softmax phase and no block barrier before the weighted sum.
+      // 4 lanes per (example, hidden quad): each sums 9 of the 36 cells, then a butterfly all-reduce
       const int k = tid >> 2, u = tid & 3;
       const int n = k / 5, hq = k - n * 5;
-      float e[kM / 4];
-      float mx = -INFINITY;
-#pragma unroll
-      for (int mm = 0; mm < kM / 4; ++mm) {
-        const int m = 4 * mm + u;
-        float sc = 0.f;
-#pragma unroll
-        for (int r = 0; r < kC; ++r) sc += xV_s[(r * kNB + n) * kM + m];
-        e[mm] = sc;
-        mx = fmaxf(mx, sc);
-      }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      float esum = 0.f;
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* kp = KV_s + (size_t)n * kM * kHS + 4 * hq;
 #pragma unroll
       for (int mm = 0; mm < kM / 4; ++mm) {
         const int m = 4 * mm + u;
-        const float a = __expf(e[mm] - mx);
-        e[mm] = a;
-        esum += a;
+        const float a = be_s[n * kM + m];
         const float4 v = lds4(kp + m * kHS);
         o.x = fmaf(a, v.x, o.x); o.y = fmaf(a, v.y, o.y); o.z = fmaf(a, v.z, o.z); o.w = fmaf(a, v.w, o.w);
       }
-      esum += __shfl_xor_sync(0xffffffffu, esum, 1);
-      esum += __shfl_xor_sync(0xffffffffu, esum, 2);
-      const float inv = 1.0f / esum;
 #pragma unroll
       for (int sh = 1; sh <= 2; sh <<= 1) {
         o.x += __shfl_xor_sync(0xffffffffu, o.x, sh);
         o.y += __shfl_xor_sync(0xffffffffu, o.y, sh);
         o.z += __shfl_xor_sync(0xffffffffu, o.z, sh);
         o.w += __shfl_xor_sync(0xffffffffu, o.w, sh);
-      }
-      o.x *= inv; o.y *= inv; o.z *= inv; o.w *= inv;
-      if (hq == 0) {   // one group per example keeps the weights: running sum over steps (aux head) and the saved beta
-        const bool counted = !GREEDY || alive_s[n] != 0;   // predict.py sums beta over generated steps only
-        float* gb = nullptr;
-        if (n < nb && rank == n % kC) {
-          if (!GREEDY) gb = p.beta + (row0 + n) * kM;
-          else if (p.g_betas && counted) gb = p.g_betas + ((size_t)(b0 + n) * p.T + t) * kM;
-        }
-#pragma unroll
-        for (int mm = 0; mm < kM / 4; ++mm) {
-          const int m = 4 * mm + u;
-          const float w = e[mm] * inv;
-          if (counted) be_s[n * kM + m] += w;
-          if (gb) gb[m] = w;
-        }
       }
       const uint32_t off = (uint32_t)(L.cvfull + n * kXS + S0 + 4 * hq) * 4u;
       st_async_f32x4(rb_u + off, o, rb_u + boff + 8u * 3);
@@ -806,10 +786,9 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     }
   }
 
-  __syncthreads();
   if (warp < nb && rank == warp % kC) {
-    p.beta_sum[(size_t)(b0 + warp) * kM + lane] = be_s[warp * kM + lane];
-    if (lane < kM - 32) p.beta_sum[(size_t)(b0 + warp) * kM + 32 + lane] = be_s[warp * kM + 32 + lane];
+    p.beta_sum[(size_t)(b0 + warp) * kM + lane] = bs0;
+    if (lane < kM - 32) p.beta_sum[(size_t)(b0 + warp) * kM + 32 + lane] = bs1;
   }
   // no CTA may exit while stores from its peers can still be in flight towards it
   cluster_barrier();
