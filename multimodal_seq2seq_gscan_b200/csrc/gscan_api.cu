@@ -884,12 +884,10 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     GSCAN_CHECK_LAUNCH();
   }
   TRY(matmul_nn(ws + L.dlogits, V, P[GSCAN_P_H2O_W], H, ws + L.dpre, H, R, H, V, 0, st));
-  TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, st));
-  // B2: output_to_hidden
+  // B2: output_to_hidden.  The two output-head weight gradients are not needed by the sweep: they are issued after
+  // it, on helper stream 1 beside the other post-sweep chains.  (Running them on a helper stream BEFORE the sweep
+  // delays the cluster launch of the sweep behind the persistent GEMM: measured 1.11 -> 1.45 ms for the sweep.)
   TRY(matmul_nn(ws + L.dpre, H, P[GSCAN_P_O2H_W], 4 * H, ws + L.dU, 4 * H, R, 4 * H, H, 0, st));
-  // (kept on the caller's stream: a persistent GEMM on a helper stream here delays the cluster launch of the
-  // sweep behind it - measured 1.11 -> 1.45 ms for the sweep)
-  TRY(launch_grad_gemm(ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H, R, sms, st));
   SideStreams* S = side_streams();
   // B3: auxiliary head
   const float* dbeta_aux = nullptr;
@@ -946,7 +944,14 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     v3::attn_value_bwd_kernel<<<dim3(B, 2), 256, smem, sv>>>(ws + L.dU + 2 * H, 4 * H, ws + L.beta, ws + L.alpha, B, Tt, Ti,
                                                              M, H, ws + L.dKV, ws + L.dKT);
     GSCAN_CHECK_LAUNCH();
-    if (S) TRY(fork_side(S, 1, sv));   // helper stream 1 continues after the value path
+    // helper stream 1: the output-head weight gradients right after the sweep, then (after the value path) the text chain
+    if (S) TRY(fork_side(S, 1, st));
+    TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
+    TRY(launch_grad_gemm(ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H, R, sms, stx));
+    if (S) {
+      TRYCUDA(cudaEventRecord(S->join_ev[0], sv));
+      TRYCUDA(cudaStreamWaitEvent(stx, S->join_ev[0], 0));
+    }
   } else {
     TRY(launch_dec_bwd(*d, bp, st));
     prof_mark(7, st);
@@ -954,6 +959,8 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       TRY(fork_side(S, 0, st));
       TRY(fork_side(S, 1, st));
     }
+    TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
+    TRY(launch_grad_gemm(ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H, R, sms, stx));
   }
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
