@@ -74,13 +74,34 @@ def bench_cfg():
 
 
 def read_peaks():
+    """Measured peaks written by the driver (MEASURED_PEAKS.json: HBM GB/s and dense bf16 TFLOP/s of this pool's
+    B200s; a value may be a number or a {burst, sustained} object - the sweep is timed inside a long step, so the
+    sustained figure applies), else the fallback of B200_PROFILING.md."""
+    fallback = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0, "source": "fallback"}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(path):
+    if not os.path.exists(path):
+        return fallback
+
+    def number(v):
+        if isinstance(v, dict):
+            for key in ("sustained", "sustained_tflops", "sustained_gbs", "value", "burst"):
+                if key in v:
+                    return float(v[key])
+            return float(next(iter(v.values())))
+        return float(v)
+
+    try:
         with open(path) as f:
             p = json.load(f)
-        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "sm_max_mhz": p.get("sm_max_mhz", 1965.0),
-                "source": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+        out = dict(fallback, source="measured")
+        for key in ("hbm_gbs", "bf16_tflops", "sm_max_mhz"):
+            for cand in (key, key + "_sustained"):
+                if cand in p:
+                    out[key] = number(p[cand])
+                    break
+        return out
+    except Exception as exc:      # a malformed file must not take the bench line down
+        return dict(fallback, source=f"fallback (MEASURED_PEAKS.json unreadable: {type(exc).__name__})")
 
 
 def read_ncu_profile():

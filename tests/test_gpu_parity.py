@@ -441,3 +441,40 @@ def test_adam_step_matches_torch():
         opt.step()
         ops.adam_step(p, g, m, v, 1e-3, 0.9, 0.999, 1e-8, step)
         assert (p - ref.detach()).abs().max() < 1e-6
+
+
+def test_fork_join_streams_keep_stream_semantics():
+    """gscan_forward / gscan_backward fork onto library-owned helper streams and join back with events; seen from the
+    caller the call must still behave like work on the ONE stream it was given: results on a side torch stream, with
+    consumers enqueued right behind on that stream and no synchronisation in between, equal the default-stream results."""
+    cfg = dict(O.CONFIGS["comp"])
+    cfg["auxiliary_task"] = True
+    params = O.synthetic_params(cfg, 5, scale=1.5)
+    batch = O.synthetic_batch(cfg, batch_size=48, seed=6, max_tgt_len=40)
+    d = to_dev(batch)
+    pos = torch.tensor(batch["target_positions"], device=DEV)
+
+    def run():
+        model = build_model(cfg, params, train=True)
+        logp, aux = model(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                          situations_input=d["situations"], target_batch=d["targets"],
+                          target_lengths=batch["tgt_lengths"])
+        loss = model.get_loss(logp, d["targets"]) + 0.3 * model.get_auxiliary_loss(aux, pos)
+        loss.backward()
+        grads = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
+        return logp.detach().clone(), grads.clone(), loss.detach().clone()
+
+    ref = run()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    outs = []
+    with torch.cuda.stream(side):
+        for _ in range(3):              # back to back: the helper streams are re-forked while earlier work is in flight
+            outs.append(run())
+    side.synchronize()
+    for logp, grads, loss in outs:
+        # split-K atomics make the weight gradients run-to-run reproducible only to fp32 rounding
+        assert torch.equal(logp, ref[0])
+        assert (grads - ref[1]).norm() <= 1e-5 * ref[1].norm()
+        assert abs(float(loss) - float(ref[2])) <= 1e-6 * abs(float(ref[2]))
