@@ -330,18 +330,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     __syncthreads();
     GSCAN3_STAMP(3);
     // ---- B2: partial dc_V (X_e) and the W_hh^T da piece of dh ----------------------------------------------
+    // (the W_hh^T da piece of dh is not needed before B12: it runs later, in the shadow of the X_b exchange, so that
+    //  the seven tiles of this critical product have the tensor pipe to themselves)
     if (warp < kTiles) {
       float o[4];
       mv_units<10>(w_tile + kUcV * 32, da_s + fg * kDaS + 2 * ft, o);
       scatter_tile(o, L.xcV, 0);
-    } else if (warp < 2 * kTiles) {
-      float o[4];
-      mv_units<10>(w_tile + kUhh * 32, da_s + fg * kDaS + 2 * ft, o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int h = 16 * tile + fg + 8 * (j >> 1);
-        if (h < kH) dhpart_s[(nF + (j & 1)) * kH + h] = o[j];
-      }
     }
     GSCAN3_STAMP(4);
     // ---- B3: the part of dalpha that does not depend on dd: da . P_gates + dU_cT . K^T --------------------------
@@ -453,6 +447,15 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
       float o[4];
       mv_units<3>(w_tile + kUqV * 32, dqV_s + fg * kVs + 2 * ft, o);
       scatter_tile(o, L.xqp, 2);
+    } else if (warp < 2 * kTiles) {
+      // the W_hh^T da piece of dh (da_s is untouched until the next cell backward), while X_b is in flight
+      float o[4];
+      mv_units<10>(w_tile + kUhh * 32, da_s + fg * kDaS + 2 * ft, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int h = 16 * tile + fg + 8 * (j >> 1);
+        if (h < kH) dhpart_s[(nF + (j & 1)) * kH + h] = o[j];
+      }
     }
     GSCAN3_STAMP(10);
     mbar_wait(bar0 + 8u * 2, par);
