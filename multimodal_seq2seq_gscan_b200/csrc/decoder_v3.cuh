@@ -462,7 +462,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       if (!GREEDY) p.Cs[(size_t)(b0 + cn) * kH + S0 + chh] = c_reg;
     }
   }
-  int my_len = 0, my_steps = 0;   // greedy bookkeeping of thread n < kNB
+  int my_len = 0, my_steps = 0;   // greedy bookkeeping of lane n < kNB of warp 15
   float bs0 = 0.f, bs1 = 0.f;   // sum over steps of beta[warp][lane], beta[warp][lane + 32]
   // Xe prefetch for the gate outputs this lane owns after its stage-A tile: rows lr0, lr0+8 x examples nF, nF+1
   const bool gate0 = roleA && lr0 >= 2 * kHS && lr0 < 6 * kHS, gate1 = roleA && lr0 + 8 >= 2 * kHS && lr0 + 8 < 6 * kHS;
@@ -483,7 +483,49 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
 
   const uint32_t bytes_xT = (uint32_t)(kC * kNB * Ti * 4), bytes_vec = (uint32_t)(kNB * kH * 4),
                  bytes_xV = (uint32_t)(kC * kNB * kM * 4);
-  int t_last = -1;   // greedy: the step at which every sequence of this cluster had ended
+  bool finished_early = false;   // greedy: every sequence of this cluster ended before the step limit
+  // greedy (predict.py:106-117), run by warp 15: wait for the logit partial sums of step s (X7), pick the token of each
+  // live example (lane n), update tok / alive / the any-alive flag; lane-private my_len / my_steps of lanes < kNB
+  auto greedy_pick = [&](int s) {
+    mbar_wait(bar0 + 8u * 5, (uint32_t)(s & 1));
+    if (lane == 0 && s + 1 < p.T) mbar_arm(bar0 + 8u * 5, (uint32_t)(kC * kNB * p.V * 4));   // for step s + 1
+    int alive_now = 0;
+    if (lane < kNB) {
+      const int n = lane, V = p.V;
+      if (alive_s[n]) {
+        const int tok = tok_s[n];
+        float l[32];   // V <= 32 in greedy mode (checked on the host)
+        float mx = -INFINITY;
+        for (int v = 0; v < V; ++v) {
+          float a = outE_s[tok * V + v];
+#pragma unroll
+          for (int r = 0; r < kC; ++r) a += xL_s[(r * kNB + n) * V + v];
+          l[v] = a;
+          mx = fmaxf(mx, a);
+        }
+        float sum = 0.f;
+        for (int v = 0; v < V; ++v) sum += expf(l[v] - mx);
+        const float lse = logf(sum);
+        float best = -INFINITY;   // first maximum of the log-softmax values, as F.log_softmax(...).max(dim=-1) gives
+        int arg = 0;
+        for (int v = 0; v < V; ++v) {
+          const float lp = (l[v] - mx) - lse;
+          if (lp > best) { best = lp; arg = v; }
+        }
+        my_steps++;
+        if (arg == p.eos) {
+          alive_s[n] = 0;
+        } else {
+          if (rank == 0) p.out_tokens[(size_t)(b0 + n) * p.T + my_len] = arg;
+          my_len++;
+        }
+        tok_s[n] = arg;
+      }
+      alive_now = alive_s[n];
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, alive_now != 0);
+    if (lane == 0) flag_s[0] = any != 0u;
+  };
 
   for (int t = 0; t < p.T; ++t) {
     const size_t row0 = (size_t)t * B + b0;   // + n
@@ -496,13 +538,23 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       mbar_arm(bar0 + 8u * 2, bytes_xV);
       mbar_arm(bar0 + 8u * 3, bytes_vec);
       if (t + 1 < p.T) mbar_arm(bar0 + 8u * 4, bytes_vec);
-      if (GREEDY) mbar_arm(bar0 + 8u * 5, (uint32_t)(kC * kNB * p.V * 4));
+      if (GREEDY && t == 0) mbar_arm(bar0 + 8u * 5, (uint32_t)(kC * kNB * p.V * 4));   // later steps: armed by greedy_pick
     }
     GSCAN3_STAMP(1);
     // ---- stage A: everything that depends only on h_{t-1} ---------------------------------------------
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (roleA) mv_tile(whi, wlo_lane, hfull_s + fg * kXS + 2 * ft, o);
+    if (GREEDY) {
+      // The token of the previous step is picked HERE, by the otherwise idle warp 15, while the role-A warps run the
+      // mat-vecs on h (which do not depend on the token); only the embedding term added below needs it.
+      if (warp == 15 && t > 0) greedy_pick(t - 1);
+      __syncthreads();
+      if (t > 0 && !flag_s[0]) {   // the same decision in every CTA of the cluster: all of them computed the same tokens
+        finished_early = true;
+        break;
+      }
+    }
     if (roleA) {
-      float o[4];
-      mv_tile(whi, wlo_lane, hfull_s + fg * kXS + 2 * ft, o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int lr = lr0 + 8 * (j >> 1), n = nF + (j & 1);
@@ -730,59 +782,16 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
           if (u == 0) st_async_f32(rb_4 + off, s, rb_4 + boff + 8u * 5);
         }
       }
-      mbar_wait(bar0 + 8u * 5, par);
-      if (tid < kNB) {
-        const int n = tid;
-        if (alive_s[n]) {
-          const int tok = tok_s[n];
-          float l[32];   // V <= 32 in greedy mode (checked on the host)
-          float mx = -INFINITY;
-          for (int v = 0; v < V; ++v) {
-            float a = outE_s[tok * V + v];
-#pragma unroll
-            for (int r = 0; r < kC; ++r) a += xL_s[(r * kNB + n) * V + v];
-            l[v] = a;
-            mx = fmaxf(mx, a);
-          }
-          float sum = 0.f;
-          for (int v = 0; v < V; ++v) sum += expf(l[v] - mx);
-          const float lse = logf(sum);
-          float best = -INFINITY;   // first maximum of the log-softmax values, as F.log_softmax(...).max(dim=-1) gives
-          int arg = 0;
-          for (int v = 0; v < V; ++v) {
-            const float lp = (l[v] - mx) - lse;
-            if (lp > best) { best = lp; arg = v; }
-          }
-          my_steps++;
-          if (arg == p.eos) {
-            alive_s[n] = 0;
-          } else {
-            if (rank == 0) p.out_tokens[(size_t)(b0 + n) * p.T + my_len] = arg;
-            my_len++;
-          }
-          tok_s[n] = arg;
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        int any = 0;
-        for (int n = 0; n < kNB; ++n) any |= alive_s[n];
-        flag_s[0] = any;
-      }
-      __syncthreads();
-      if (!flag_s[0]) {   // the same decision in every CTA of the cluster: all of them computed the same tokens
-        t_last = t;
-        break;
-      }
     }
     GSCAN3_STAMP(15);
   }
   if (GREEDY) {
-    // stores of h_t towards this CTA issued in the last executed step must land before it may exit
-    if (t_last >= 0 && t_last + 1 < p.T) mbar_wait(bar0 + 8u * 4, (uint32_t)(t_last & 1));
-    if (rank == 0 && tid < nb) {
-      p.out_len[b0 + tid] = my_len;
-      p.out_steps[b0 + tid] = my_steps;
+    // (an early exit happens right after the h of the last executed step has been received, before anything of the
+    //  next step is sent, so nothing is in flight towards this CTA; after a full run the last token is still to be picked)
+    if (!finished_early && warp == 15) greedy_pick(p.T - 1);
+    if (rank == 0 && warp == 15 && lane < nb) {
+      p.out_len[b0 + lane] = my_len;
+      p.out_steps[b0 + lane] = my_steps;
     }
   }
 
