@@ -1138,26 +1138,32 @@ int gscan_greedy_decode(const gscan_dims* d, const float* const* P, const int64_
   float* Wout = XeTab + pad4(V * 4 * H);
   float* OutE = Wout + pad4(V * 4 * H);
   float* Wo_t = OutE + pad4(V * V);
-  TRY(run_encoder_side(e, P, reinterpret_cast<const long long*>(commands), cmd_len, situations, nullptr, nullptr, ws,
-                       L, true, st));
-  TRY(pack_decoder_weights(e, P, ws, L, st));
+  // everything that depends on the weights only (packed decoder weights, eval-mode tables, the token buffer fill)
+  // runs on helper stream 1 beside the encoder side
+  SideStreams* S = side_streams();
+  cudaStream_t sp = S ? S->s[1] : st;
+  if (S) TRY(fork_side(S, 1, st));
+  TRY(pack_decoder_weights(e, P, ws, L, sp));
   // eval-mode tables: the embedding-dependent parts of the gates and of the logits have only V rows
   TRY(linear(P[GSCAN_P_DEC_EMB], H, P[GSCAN_P_DEC_WIH], 3 * H, XeTab, 4 * H, V, 4 * H, H, P[GSCAN_P_DEC_BIH],
-             P[GSCAN_P_DEC_BHH], 0, st));
-  TRY(matmul_nn(P[GSCAN_P_H2O_W], H, P[GSCAN_P_O2H_W], 4 * H, Wout, 4 * H, V, 4 * H, H, 0, st));
-  TRY(linear(P[GSCAN_P_DEC_EMB], H, Wout, 4 * H, OutE, V, V, V, H, nullptr, nullptr, 0, st));
-  TRYCUDA(cudaMemsetAsync(Wo_t, 0, sizeof(float) * 3 * H * Vp, st));
+             P[GSCAN_P_DEC_BHH], 0, sp));
+  TRY(matmul_nn(P[GSCAN_P_H2O_W], H, P[GSCAN_P_O2H_W], 4 * H, Wout, 4 * H, V, 4 * H, H, 0, sp));
+  TRY(linear(P[GSCAN_P_DEC_EMB], H, Wout, 4 * H, OutE, V, V, V, H, nullptr, nullptr, 0, sp));
+  TRYCUDA(cudaMemsetAsync(Wo_t, 0, sizeof(float) * 3 * H * Vp, sp));
   {
     PackTable tab;
     tab.n = 1;
     tab.d[0] = PackDesc{Wout, 4 * H, H, Wo_t, Vp, 0, V, 3 * H};
-    TRY(launch_pack(tab, st));
+    TRY(launch_pack(tab, sp));
   }
   {
     long n = (long)B * T;
-    fill_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<long long*>(out_tokens), n, -1);
+    fill_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sp>>>(reinterpret_cast<long long*>(out_tokens), n, -1);
     GSCAN_CHECK_LAUNCH();
   }
+  TRY(run_encoder_side(e, P, reinterpret_cast<const long long*>(commands), cmd_len, situations, nullptr, nullptr, ws,
+                       L, true, st));
+  if (S) TRY(join_side(S, 1, st));
   DecFwdP p{};
   fill_dec_fwd_common(e, P, ws, L, p);
   p.T = T;
