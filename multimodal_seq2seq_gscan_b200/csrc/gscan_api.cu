@@ -12,6 +12,7 @@
 #include "gemm.cuh"
 #include "misc.cuh"
 #include "recurrent.cuh"
+#include "encoder_res.cuh"
 #include "decoder_cluster.cuh"
 #include "decoder_v3.cuh"
 #include "decoder_v3_bwd.cuh"
@@ -268,7 +269,27 @@ int enc_nb(const gscan_dims& d) {
   return nb;
 }
 
+// Resident-weight encoder sweeps (encoder_res.cuh) when W_hh of one direction fits in shared memory beside the
+// partial-sum scratch; GSCAN_ENC_STREAMING=1 forces the L2-streaming kernels (A/B measurements, tests).
+template <int NB>
+int launch_enc_res(const gscan_dims& d, const EncP& p, bool bwd, cudaStream_t st, bool* done) {
+  *done = false;
+  static const bool force_streaming = getenv("GSCAN_ENC_STREAMING") != nullptr;
+  if (force_streaming || NB * d.H > kRecThreads || !enc_res_slices_ok(d.H, kRecThreads)) return 0;
+  const size_t by = enc_res_smem_floats<NB>(d.H, kRecThreads, bwd) * sizeof(float);
+  if (by > kMaxSmemBytes) return 0;
+  dim3 grid(ceil_div(d.B, NB), 2);
+  if (bwd) { TRY(set_smem(encoder_bwd_res_kernel<NB>, by)); encoder_bwd_res_kernel<NB><<<grid, kRecThreads, by, st>>>(p); }
+  else { TRY(set_smem(encoder_fwd_res_kernel<NB>, by)); encoder_fwd_res_kernel<NB><<<grid, kRecThreads, by, st>>>(p); }
+  GSCAN_CHECK_LAUNCH();
+  *done = true;
+  return 0;
+}
+
 int launch_enc(const gscan_dims& d, const EncP& p, bool bwd, cudaStream_t st) {
+  bool done = false;
+  TRY(launch_enc_res<4>(d, p, bwd, st, &done));
+  if (done) return 0;
   int nb = enc_nb(d);
   dim3 grid(ceil_div(d.B, nb), 2);
   if (nb == 2) {
