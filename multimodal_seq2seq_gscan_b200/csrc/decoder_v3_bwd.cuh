@@ -633,5 +633,94 @@ __global__ void __launch_bounds__(256) attn_value_bwd_kernel(const float* __rest
   }
 }
 
+// ---- after the sweep: value path of both attentions, reordered so that nothing of size [Tt*B] is multiplied ----
+//   dK^V[b, m, :] += sum_t beta[t, b, m]  * dc_V[t, b, :],   dK^T[j, b, :] += sum_t alpha[t, b, j] * dc_T[t, b, :]
+// where dc_V[t, b, :] = X[t, b, :] . Wst_V and dc_T[t, b, :] = X[t, b, :] . Wst_T are linear in the row
+// X = [dgates (4H) | dpre (H) | dd (H)] (LSTM input block, output head, conditional query).  Summing over t FIRST,
+//   Z_V[b, m, :] = sum_t beta[t, b, m] X[t, b, :]        (per example a [36 x Tt] . [Tt x 5H] product)
+//   Z_T[j, b, :] = sum_t alpha[t, b, j] X[t, b, :]       ([Ti x Tt] . [Tt x 6H])
+// turns the two [Tt*B x 4H] x [4H x 2H] products + attn_value_bwd_kernel of the first version (166 us on the
+// critical path after the sweep) into this one memory-bound pass over X plus two small products
+// dK^V += Z_V . Wst_V ([B*36 x 5H] . [5H x H]) and dK^T += Z_T . Wst_T ([Ti*B x 6H] . [6H x H]).
+struct ValueZP {
+  const float *dgates, *dpre, *dd;   // [T*B][4H], [T*B][H], [T*B][H] (dd null without conditional attention)
+  const float *alpha, *beta;         // [T][B][Ti], [T][B][36]
+  int B, T, Ti, H, NC;               // NC = 5H or 6H columns of X
+  float *ZV, *ZT;                    // [B*36][ldv], [Ti*B][ldt]
+  int ldv, ldt;
+};
+constexpr int kZW = kM + kMaxTi;     // weights per step: 36 beta | up to 16 alpha (zero padded)
+
+// grid = (B, ceil(NC / 256)); thread = one column of X for one example, 52 accumulators
+__global__ void __launch_bounds__(256) attn_value_z_kernel(ValueZP p) {
+  extern __shared__ __align__(16) float zw_s[];   // [T][kZW]
+  const int b = blockIdx.x, B = p.B, T = p.T, Ti = p.Ti, H = p.H;
+  for (int i = threadIdx.x; i < T * kZW; i += blockDim.x) {
+    const int t = i / kZW, k = i - t * kZW;
+    float v = 0.f;
+    if (k < kM) v = __ldg(p.beta + ((size_t)t * B + b) * kM + k);
+    else if (k - kM < Ti) v = __ldg(p.alpha + ((size_t)t * B + b) * Ti + (k - kM));
+    zw_s[i] = v;
+  }
+  __syncthreads();
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= p.NC) return;
+  const float* src;
+  size_t ld;
+  if (c < 4 * H) { src = p.dgates + c; ld = 4 * (size_t)H; }
+  else if (c < 5 * H) { src = p.dpre + (c - 4 * H); ld = H; }
+  else { src = p.dd + (c - 5 * H); ld = H; }
+  src += (size_t)b * ld;
+  const size_t step = (size_t)B * ld;
+  float acc[kZW];
+#pragma unroll
+  for (int k = 0; k < kZW; ++k) acc[k] = 0.f;
+  for (int t0 = 0; t0 < T; t0 += 4) {
+    float x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = (t0 + u < T) ? __ldg(src + (size_t)(t0 + u) * step) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u < T) {
+        const float4* w = reinterpret_cast<const float4*>(zw_s + (t0 + u) * kZW);
+#pragma unroll
+        for (int q = 0; q < kZW / 4; ++q) {
+          const float4 wv = w[q];
+          acc[4 * q] = fmaf(wv.x, x[u], acc[4 * q]);
+          acc[4 * q + 1] = fmaf(wv.y, x[u], acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(wv.z, x[u], acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(wv.w, x[u], acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  if (c < p.ldv) {
+#pragma unroll
+    for (int m = 0; m < kM; ++m) p.ZV[((size_t)b * kM + m) * p.ldv + c] = acc[m];
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxTi; ++j)
+    if (j < Ti) p.ZT[((size_t)j * B + b) * p.ldt + c] = acc[kM + j];
+}
+
+// Wst_V [5H][H] = [W_ih[:, 2H:3H] ; W_o2h[:, 3H:4H]],  Wst_T [6H][H] = [W_ih[:, H:2H] ; W_o2h[:, 2H:3H] ; W_c[:, H:2H]]
+__global__ void value_weight_stack_kernel(const float* __restrict__ W_ih, const float* __restrict__ W_o2h,
+                                          const float* __restrict__ W_c, int H, float* __restrict__ WstV,
+                                          float* __restrict__ WstT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nV = 5 * H * H, nT = (W_c ? 6 : 5) * H * H;
+  if (i < nV) {
+    const int r = i / H, j = i - r * H;
+    WstV[i] = r < 4 * H ? __ldg(W_ih + (size_t)r * 3 * H + 2 * H + j) : __ldg(W_o2h + (size_t)(r - 4 * H) * 4 * H + 3 * H + j);
+  } else if (i < nV + nT) {
+    const int k = i - nV, r = k / H, j = k - r * H;
+    float v;
+    if (r < 4 * H) v = __ldg(W_ih + (size_t)r * 3 * H + H + j);
+    else if (r < 5 * H) v = __ldg(W_o2h + (size_t)(r - 4 * H) * 4 * H + 2 * H + j);
+    else v = __ldg(W_c + (size_t)(r - 5 * H) * 2 * H + H + j);
+    WstT[k] = v;
+  }
+}
+
 }  // namespace v3
 }  // namespace gscan

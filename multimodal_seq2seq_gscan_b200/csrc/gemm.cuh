@@ -337,6 +337,26 @@ inline int launch_grad_gemm(const float* X, long ldx, const float* Y, long ldy, 
   return launch_sgemm(X, 1, ldx, Y, ldy, 1, C, ldc, N1, N2, R, nullptr, nullptr, 0, 0, ksplit, st);
 }
 
+// A family of weight-gradient products over the same R rows: the ones the tcgen05 kernel can address go out as ONE
+// grouped launch (tc::launch_group_tn), the rest one by one.
+inline int launch_grad_group(const tc::GroupProblem* probs, int n, int R, int num_sms, cudaStream_t st) {
+  tc::GroupProblem grouped[tc::MAXG];
+  int ng = 0;
+  static const bool no_group = getenv("GSCAN_NO_GROUP_GEMM") != nullptr;
+  for (int i = 0; i < n; ++i) {
+    const tc::GroupProblem& q = probs[i];
+    if (!no_group && ng < tc::MAXG && use_tc(q.X, 1, q.ldx, q.Y, q.ldy, 1, q.N1, q.N2, R)) {
+      grouped[ng++] = q;
+    } else {
+      int rc = launch_grad_gemm(q.X, q.ldx, q.Y, q.ldy, q.C, q.ldc, q.N1, q.N2, R, num_sms, st);
+      if (rc) return rc;
+    }
+  }
+  if (ng == 1) return launch_grad_gemm(grouped[0].X, grouped[0].ldx, grouped[0].Y, grouped[0].ldy, grouped[0].C,
+                                       grouped[0].ldc, grouped[0].N1, grouped[0].N2, R, num_sms, st);
+  return tc::launch_group_tn(grouped, ng, R, st);
+}
+
 // out[j] = sum_r X[r*ldx + j]  for j < N  (bias gradients).  out is overwritten.
 __global__ void colsum_kernel(const float* __restrict__ X, long ldx, int R, int N, int rows_per_block,
                               float* __restrict__ out) {

@@ -29,6 +29,8 @@
 //                                   after the last K-block: bias/act -> coalesced global stores (atomicAdd for split-K)
 #pragma once
 #include <cuda.h>
+#include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gscan {
@@ -61,6 +63,17 @@ struct Params {
   int ksplit;
   uint32_t mn_layout, mn_sbo, mn_lbo;   // descriptor fields of an MN-major operand
   long long* timeline;                  // optional [4 roles][128] clock64 stamps of CTA 0 (tools/tc_gemm_dev.cu)
+};
+// Grouped launch: several products that share K (and the operand majors) walk ONE persistent tile list, so that a
+// family of small weight-gradient products costs one launch, one pipeline fill and one wave of split-K atomics.
+constexpr int MAXG = 12;
+struct alignas(64) GroupMaps { CUtensorMap a[MAXG]; CUtensorMap b[MAXG]; };
+struct GroupTable {
+  float* C[MAXG]; long ldc[MAXG];
+  int M[MAXG], N[MAXG];
+  int n_tiles[MAXG];   // N tiles of problem g
+  int mn_end[MAXG];    // cumulative count of (m, n) tiles up to and including problem g
+  int ng;
 };
 #ifndef TC_VEC_STORE
 #define TC_VEC_STORE 0
@@ -219,9 +232,11 @@ __device__ __forceinline__ void store_rows_v4(float* dst, long ldc, const float*
   }
 }
 
-template <bool AK, bool BKM>   // operand contiguous along K in global memory (else along M / N)
-__global__ void __launch_bounds__(THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+// AK / BKM: operand contiguous along K in global memory (else along M / N).  GROUP: tmA / tmB are arrays indexed by
+// the problem number and the per-problem shapes come from `gt` (Params then carries only the shared K split).
+template <bool AK, bool BKM, bool GROUP>
+__device__ __forceinline__ void tc_body(const CUtensorMap* tmA, const CUtensorMap* tmB, const Params& p,
+                                        const GroupTable* gt) {
   extern __shared__ uint8_t tc_smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -236,8 +251,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bar0 + 8u * (3 * STAGES + 2 * ACC_BUFS);
 
   if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    const int nmaps = GROUP ? gt->ng : 1;
+    for (int g = 0; g < nmaps; ++g) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(tmA + g) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(tmB + g) : "memory");
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_raw(s), 1);
       mbar_init(full_cvt(s), CVT_THREADS);
@@ -261,23 +279,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   // persistent static schedule: tile = ((m-tile * n_tiles + n-tile) * ksplit + z); every role walks the same list
   const int n_tiles = ceil_div(p.N, BN);
-  const int total_tiles = ceil_div(p.M, BM) * n_tiles * p.ksplit;
-  auto tile_coords = [&](int tile, int& m0, int& n0, int& kb0, int& nkb) {
+  const int total_tiles = (GROUP ? gt->mn_end[gt->ng - 1] : ceil_div(p.M, BM) * n_tiles) * p.ksplit;
+  auto tile_coords = [&](int tile, int& g, int& m0, int& n0, int& kb0, int& nkb) {
     const int z = tile % p.ksplit;
-    const int mn = tile / p.ksplit;
-    m0 = (mn / n_tiles) * BM;
-    n0 = (mn % n_tiles) * BN;
+    int mn = tile / p.ksplit;
+    g = 0;
+    int nt = n_tiles;
+    if (GROUP) {
+      while (mn >= gt->mn_end[g]) ++g;
+      if (g > 0) mn -= gt->mn_end[g - 1];
+      nt = gt->n_tiles[g];
+    }
+    m0 = (mn / nt) * BM;
+    n0 = (mn % nt) * BN;
     kb0 = z * p.kb_per;
     nkb = min(p.kb_total, kb0 + p.kb_per) - kb0;
   };
+  auto prob_M = [&](int g) { return GROUP ? gt->M[g] : p.M; };
+  auto prob_N = [&](int g) { return GROUP ? gt->N[g] : p.N; };
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int g = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int m0, n0, kb0, nkb;
-        tile_coords(tile, m0, n0, kb0, nkb);
+        int g_, m0, n0, kb0, nkb;
+        tile_coords(tile, g_, m0, n0, kb0, nkb);
         for (int it = 0; it < nkb; ++it, ++g) {
           const int s = g % STAGES;
           mbar_wait(empty(s), ((g / STAGES) & 1) ^ 1);
@@ -286,18 +313,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int k = (kb0 + it) * BK;
           mbar_arrive_expect_tx(full_raw(s), 2 * TILE_BYTES);
           if (AK) {
-            tma_load_2d(st, &tmA, k, m0, full_raw(s));                       // box [32 k][128 rows]
+            tma_load_2d(st, tmA + g_, k, m0, full_raw(s));                       // box [32 k][128 rows]
           } else {
 #pragma unroll
             for (int q = 0; q < BM / 32; ++q)                                // 4 boxes [32 m][32 k]
-              tma_load_2d(st + q * (BK * 128), &tmA, m0 + 32 * q, k, full_raw(s));
+              tma_load_2d(st + q * (BK * 128), tmA + g_, m0 + 32 * q, k, full_raw(s));
           }
           if (BKM) {
-            tma_load_2d(st + 2 * TILE_BYTES, &tmB, k, n0, full_raw(s));
+            tma_load_2d(st + 2 * TILE_BYTES, tmB + g_, k, n0, full_raw(s));
           } else {
 #pragma unroll
             for (int q = 0; q < BN / 32; ++q)
-              tma_load_2d(st + 2 * TILE_BYTES + q * (BK * 128), &tmB, n0 + 32 * q, k, full_raw(s));
+              tma_load_2d(st + 2 * TILE_BYTES + q * (BK * 128), tmB + g_, n0 + 32 * q, k, full_raw(s));
           }
         }
       }
@@ -307,9 +334,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int g = 0, w = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int m0, n0, kb0, nkb;
-        tile_coords(tile, m0, n0, kb0, nkb);
-        const int n_valid = min(BN, p.N - n0);
+        int g_, m0, n0, kb0, nkb;
+        tile_coords(tile, g_, m0, n0, kb0, nkb);
+        const int n_valid = min(BN, prob_N(g_) - n0);
         const uint32_t idesc = make_idesc(!AK, !BKM, min(BN, (n_valid + 15) & ~15));
         int in_win = 0;
         for (int it = 0; it < nkb; ++it, ++g) {
@@ -352,8 +379,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ct = threadIdx.x - 64;
     int g = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int m0, n0, kb0, nkb;
-      tile_coords(tile, m0, n0, kb0, nkb);
+      int g_, m0, n0, kb0, nkb;
+      tile_coords(tile, g_, m0, n0, kb0, nkb);
       for (int it = 0; it < nkb; ++it, ++g) {
         const int s = g % STAGES;
         mbar_wait(full_raw(s), (g / STAGES) & 1);
@@ -393,9 +420,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool split = p.ksplit > 1;
     int w = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int m0, n0, kb0, nkb;
-      tile_coords(tile, m0, n0, kb0, nkb);
-      const int n_valid = min(BN, p.N - n0);
+      int g_, m0, n0, kb0, nkb;
+      tile_coords(tile, g_, m0, n0, kb0, nkb);
+      const int n_valid = min(BN, prob_N(g_) - n0);
       const int nwin = ceil_div(nkb, FLUSH);
       float acc[BN];
 #pragma unroll
@@ -420,8 +447,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // write-out: per-warp 32x32 transpose through shared memory so that every global access is a full 128-B row segment
       const int mode = split ? 4 : (p.accumulate ? 3 : p.act);     // warp-uniform
-      const int rows = min(32, p.M - (m0 + 32 * q));
-      const bool vec = TC_VEC_STORE && ((p.ldc & 3) == 0) && ((p.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      const int rows = min(32, prob_M(g_) - (m0 + 32 * q));
+      float* const Cg = GROUP ? gt->C[g_] : p.C;
+      const long ldcg = GROUP ? gt->ldc[g_] : p.ldc;
+      const int Ng = prob_N(g_);
+      const bool vec = TC_VEC_STORE && ((ldcg & 3) == 0) && ((Ng & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cg) & 15) == 0);
       int tl_i = 5 * ((tile - blockIdx.x) / gridDim.x);
       if (threadIdx.x == 192) TC_STAMP(4, tl_i);
 #pragma unroll
@@ -436,18 +466,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             const int gn = n0 + c * 32 + (lane & 7) * 4;
             float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (!split && gn < p.N) {
+            if (!split && gn < Ng) {
               if (p.bias) { const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + gn)); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
               if (p.bias2) { const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias2 + gn)); bsum.x += b.x; bsum.y += b.y; bsum.z += b.z; bsum.w += b.w; }
             }
-            float* dst = p.C + (long)(m0 + 32 * q) * p.ldc + n0 + c * 32;
+            float* dst = Cg + (long)(m0 + 32 * q) * ldcg + n0 + c * 32;
             const int cols = n_valid - c * 32;
             switch (mode) {
-              case 0: store_rows_v4<0>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
-              case 1: store_rows_v4<1>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
-              case 2: store_rows_v4<2>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
-              case 3: store_rows_v4<3>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
-              default: store_rows_v4<4>(dst, p.ldc, stage_out, lane, rows, cols, bsum); break;
+              case 0: store_rows_v4<0>(dst, ldcg, stage_out, lane, rows, cols, bsum); break;
+              case 1: store_rows_v4<1>(dst, ldcg, stage_out, lane, rows, cols, bsum); break;
+              case 2: store_rows_v4<2>(dst, ldcg, stage_out, lane, rows, cols, bsum); break;
+              case 3: store_rows_v4<3>(dst, ldcg, stage_out, lane, rows, cols, bsum); break;
+              default: store_rows_v4<4>(dst, ldcg, stage_out, lane, rows, cols, bsum); break;
             }
           } else {
 #pragma unroll
@@ -455,20 +485,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (threadIdx.x == 192) TC_STAMP(4, 64 + tl_i + 1 + c);
             const int gn = n0 + c * 32 + lane;
-            if (gn < p.N) {
+            if (gn < Ng) {
               float bsum = 0.f;
               if (!split) {
                 if (p.bias) bsum += __ldg(p.bias + gn);
                 if (p.bias2) bsum += __ldg(p.bias2 + gn);
               }
-              float* dst = p.C + (long)(m0 + 32 * q) * p.ldc + gn;
+              float* dst = Cg + (long)(m0 + 32 * q) * ldcg + gn;
               const float* src = stage_out + lane;
               switch (mode) {
-                case 0: store_rows<0>(dst, p.ldc, src, rows, bsum); break;
-                case 1: store_rows<1>(dst, p.ldc, src, rows, bsum); break;
-                case 2: store_rows<2>(dst, p.ldc, src, rows, bsum); break;
-                case 3: store_rows<3>(dst, p.ldc, src, rows, bsum); break;
-                default: store_rows<4>(dst, p.ldc, src, rows, bsum); break;
+                case 0: store_rows<0>(dst, ldcg, src, rows, bsum); break;
+                case 1: store_rows<1>(dst, ldcg, src, rows, bsum); break;
+                case 2: store_rows<2>(dst, ldcg, src, rows, bsum); break;
+                case 3: store_rows<3>(dst, ldcg, src, rows, bsum); break;
+                default: store_rows<4>(dst, ldcg, src, rows, bsum); break;
               }
             }
           }
@@ -484,6 +514,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
+}
+
+template <bool AK, bool BKM>
+__global__ void __launch_bounds__(THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  tc_body<AK, BKM, false>(&tmA, &tmB, p, nullptr);
+}
+
+// "TN" weight-gradient family: C_g[M_g, N_g] += sum_r X_g[r, i] * Y_g[r, j] for every problem g, all over the same R rows
+__global__ void __launch_bounds__(THREADS, 1)
+tc_group_tn_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ GroupTable gt, const Params p) {
+  tc_body<false, false, true>(maps.a, maps.b, p, &gt);
+}
+
+// zero the destination blocks of a group before its split-K atomics (one launch for all of them)
+__global__ void group_zero_kernel(const __grid_constant__ GroupTable gt) {
+  const int g = blockIdx.y;
+  if (g >= gt.ng) return;
+  const int M = gt.M[g], N = gt.N[g];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * N; i += gridDim.x * blockDim.x)
+    gt.C[g][(long)(i / N) * gt.ldc[g] + (i % N)] = 0.f;
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -578,6 +629,66 @@ inline int launch(const float* A, long a_rs, long a_cs, const float* B, long b_r
   if (ak && !bk) return launch_t<true, false>(ta, tb, p, grid, st);
   if (!ak && bk) return launch_t<false, true>(ta, tb, p, grid, st);
   return launch_t<false, false>(ta, tb, p, grid, st);
+}
+
+// One weight-gradient problem of a group: C[N1, N2] (ldc) = sum_r X[r, i] * Y[r, j], X [R][ldx], Y [R][ldy].
+struct GroupProblem { const float* X; long ldx; const float* Y; long ldy; float* C; long ldc; int N1, N2; };
+
+inline bool group_eligible(const GroupProblem& q, int R) { return eligible(q.X, 1, q.ldx, q.Y, q.ldy, 1, q.N1, q.N2, R); }
+
+// All problems in ONE persistent launch (plus one launch that zeroes the destinations).  The tensor maps are
+// rebuilt only when a pointer or shape changed since the previous call (the workspace is stable across steps).
+inline int launch_group_tn(const GroupProblem* probs, int n, int R, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n > MAXG) return -3;
+  struct Cache { GroupProblem key[MAXG]; int n = 0, R = 0; GroupMaps maps; };
+  static thread_local Cache cache;
+  const MnConfig& mc = mn_config();
+  const CUtensorMapSwizzle mn_swz = (CUtensorMapSwizzle)mc.tma_swizzle;
+  bool same = cache.n == n && cache.R == R;
+  for (int g = 0; same && g < n; ++g) same = memcmp(&cache.key[g], &probs[g], sizeof(GroupProblem)) == 0;
+  if (!same) {
+    cache.n = 0;
+    for (int g = 0; g < n; ++g) {
+      int rc = make_map(&cache.maps.a[g], probs[g].X, probs[g].N1, R, probs[g].ldx, BK, mn_swz);
+      if (rc) return rc;
+      rc = make_map(&cache.maps.b[g], probs[g].Y, probs[g].N2, R, probs[g].ldy, BK, mn_swz);
+      if (rc) return rc;
+      memset(&cache.key[g], 0, sizeof(GroupProblem));
+      cache.key[g] = probs[g];
+    }
+    cache.n = n;
+    cache.R = R;
+  }
+  GroupTable gt{};
+  int mn = 0;
+  for (int g = 0; g < n; ++g) {
+    gt.C[g] = probs[g].C; gt.ldc[g] = probs[g].ldc; gt.M[g] = probs[g].N1; gt.N[g] = probs[g].N2;
+    gt.n_tiles[g] = ceil_div(probs[g].N2, BN);
+    mn += ceil_div(probs[g].N1, BM) * gt.n_tiles[g];
+    gt.mn_end[g] = mn;
+  }
+  gt.ng = n;
+  Params p{nullptr, 0, 0, 0, R, nullptr, nullptr, 0, 0, 0, 0, 1, mc.layout, mc.sbo, mc.lbo, nullptr};
+  p.kb_total = ceil_div(R, BK);
+  // one persistent wave; GSCAN_GROUP_SM_LIMIT leaves the other SMs to kernels of concurrent streams
+  static const int sm_limit = getenv("GSCAN_GROUP_SM_LIMIT") ? atoi(getenv("GSCAN_GROUP_SM_LIMIT")) : 0;
+  const int sms = (sm_limit > 0 && mn * 4 <= sm_limit) ? min(sm_limit, num_sms()) : num_sms();
+  int ksplit = max(1, min(ceil_div(R, 4 * BK), sms / mn));
+  p.kb_per = ceil_div(p.kb_total, ksplit);
+  p.ksplit = ceil_div(p.kb_total, p.kb_per);
+  group_zero_kernel<<<dim3(16, n), 256, 0, st>>>(gt);
+  GSCAN_CHECK_LAUNCH();
+  if (p.ksplit == 1) p.accumulate = 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tc_group_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  tc_group_tn_kernel<<<min(mn * p.ksplit, sms), THREADS, SMEM_BYTES, st>>>(cache.maps, gt, p);
+  GSCAN_CHECK_LAUNCH();
+  return 0;
 }
 
 }  // namespace tc

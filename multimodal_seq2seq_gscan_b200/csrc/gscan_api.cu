@@ -78,7 +78,11 @@ SideStreams* side_streams() {
   SideStreams& S = per_device[dev];
   if (!S.ok) {
     for (int i = 0; i < 2; ++i) {
-      if (cudaStreamCreateWithFlags(&S.s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      // highest priority: the helper chains are long sequences of small kernels, and their CTAs must not queue
+      // behind the persistent GEMMs of the caller's stream whenever an SM has room for them
+      int prio_lo = 0, prio_hi = 0;
+      if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_hi = 0;
+      if (cudaStreamCreateWithPriority(&S.s[i], cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&S.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&S.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
@@ -115,6 +119,7 @@ struct Layout {
   // backward scratch
   size_t dlogits, dpre, dU, dgates, dd, dqV, dqT, dKT, dKV, dh0, dbeta_aux, dfeat, dconv, dWt_cnn;
   size_t denc_out, dh_enc, dpre0, dga[2], hprev[2], denc_x, dvec;
+  size_t ZV, ZT, WstV, WstT;   // reordered value path of the attentions (v3::attn_value_z_kernel)
   int RA, RB;
 };
 
@@ -173,6 +178,10 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
     L.dfeat = L.take(B * M * D);
     L.dconv = L.take(B * M * D);
     L.dWt_cnn = L.take(cs.wtotal());
+    L.ZV = L.take(B * M * 5 * H);
+    L.ZT = L.take(Ti * B * 6 * H);
+    L.WstV = L.take(5 * H * H);
+    L.WstT = L.take(6 * H * H);
     L.denc_out = L.take(Ti * B * H);
     L.dh_enc = L.take(B * H);
     L.dpre0 = L.take(B * H);
@@ -952,26 +961,37 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   //   helper stream 0  value path of both attentions (dc_T, dc_V -> dK^V, dK^T), then visual keys -> CNN
   //   helper stream 1  (after the value path) textual keys -> initial state -> command encoder
   cudaStream_t sv = S ? S->s[0] : st, stx = S ? S->s[1] : st;
+  bool wait_value_path = false;
   if (bwd_v3) {
     prof_mark(7, st);   // the sweep kernel alone; what follows counts as batched weight-gradient work
     if (S) TRY(fork_side(S, 0, st));
-    // value path of both attentions, outside the recurrence: dc_T, dc_V for all steps as batched products,
-    // accumulated into the (already consumed) [c_T | c_V] columns of dU, then dK += sum_t w_t dc_t
-    TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH] + H, 3 * H, ws + L.dU + 2 * H, 4 * H, R, 2 * H, 4 * H, 1, sv));
-    if (d->conditional_attention)
-      TRY(matmul_nn(ws + L.dd, H, P[GSCAN_P_COND_W] + H, 2 * H, ws + L.dU + 2 * H, 4 * H, R, H, H, 1, sv));
-    size_t smem = sizeof(float) * (size_t)Tt * ((((M > Ti ? M : Ti) + 3) & ~3) + H);
-    if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_bwd_kernel, smem));
-    v3::attn_value_bwd_kernel<<<dim3(B, 2), 256, smem, sv>>>(ws + L.dU + 2 * H, 4 * H, ws + L.beta, ws + L.alpha, B, Tt, Ti,
-                                                             M, H, ws + L.dKV, ws + L.dKT);
-    GSCAN_CHECK_LAUNCH();
+    // value path of both attentions, outside the recurrence and summed over time first (decoder_v3_bwd.cuh):
+    // Z = sum_t w_t (x) [dgates | dpre | dd], then dK += Z . Wst
+    {
+      const int NC = (d->conditional_attention ? 6 : 5) * H;
+      const int nst = 5 * H * H + NC * H;
+      v3::value_weight_stack_kernel<<<ceil_div(nst, 256), 256, 0, sv>>>(
+          P[GSCAN_P_DEC_WIH], P[GSCAN_P_O2H_W], d->conditional_attention ? P[GSCAN_P_COND_W] : nullptr, H, ws + L.WstV,
+          ws + L.WstT);
+      GSCAN_CHECK_LAUNCH();
+      v3::ValueZP zp{};
+      zp.dgates = ws + L.dgates; zp.dpre = ws + L.dpre; zp.dd = ws + L.dd;
+      zp.alpha = ws + L.alpha; zp.beta = ws + L.beta;
+      zp.B = B; zp.T = Tt; zp.Ti = Ti; zp.H = H; zp.NC = NC;
+      zp.ZV = ws + L.ZV; zp.ZT = ws + L.ZT; zp.ldv = 5 * H; zp.ldt = NC;
+      size_t smem = sizeof(float) * (size_t)Tt * v3::kZW;
+      if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel, smem));
+      v3::attn_value_z_kernel<<<dim3(B, ceil_div(NC, 256)), 256, smem, sv>>>(zp);
+      GSCAN_CHECK_LAUNCH();
+      TRY(matmul_nn(ws + L.ZV, 5 * H, ws + L.WstV, H, ws + L.dKV, H, B * M, H, 5 * H, 1, sv));
+      TRY(matmul_nn(ws + L.ZT, NC, ws + L.WstT, H, ws + L.dKT, H, Ti * B, H, NC, 1, sv));
+    }
     // helper stream 1: the output-head weight gradients right after the sweep, then (after the value path) the text chain
     if (S) TRY(fork_side(S, 1, st));
     TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
-    TRY(launch_grad_gemm(ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H, R, sms, stx));
     if (S) {
-      TRYCUDA(cudaEventRecord(S->join_ev[0], sv));
-      TRYCUDA(cudaStreamWaitEvent(stx, S->join_ev[0], 0));
+      TRYCUDA(cudaEventRecord(S->join_ev[0], sv));   // value path done: dK^T, dK^V complete
+      wait_value_path = true;
     }
   } else {
     TRY(launch_dec_bwd(*d, bp, st));
@@ -981,24 +1001,30 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       TRY(fork_side(S, 1, st));
     }
     TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
-    TRY(launch_grad_gemm(ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H, R, sms, stx));
   }
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
-  // B5: decoder weight gradients as batched "TN" products over all steps
+  // B5: decoder weight gradients (and the output_to_hidden one) as "TN" products over all R = Tt*B rows: ONE grouped
+  // tcgen05 launch (24 output tiles x 6 K-splits = one wave of 144 CTAs) instead of nine split-K launches
   const float* Hprev = U0 + H;       // rows t*B+b hold h_{t-1}
-  TRY(launch_grad_gemm(ws + L.dgates, 4 * H, U1, 4 * H, G[GSCAN_P_DEC_WIH], 3 * H, 4 * H, H, R, sms, st));
-  TRY(launch_grad_gemm(ws + L.dgates, 4 * H, U1 + 2 * H, 4 * H, G[GSCAN_P_DEC_WIH] + H, 3 * H, 4 * H, 2 * H, R, sms, st));
-  TRY(launch_grad_gemm(ws + L.dgates, 4 * H, Hprev, 4 * H, G[GSCAN_P_DEC_WHH], H, 4 * H, H, R, sms, st));
+  {
+    tc::GroupProblem gp[tc::MAXG];
+    int n = 0;
+    gp[n++] = {ws + L.dgates, 4 * H, U1, 4 * H, G[GSCAN_P_DEC_WIH], 3 * H, 4 * H, H};
+    gp[n++] = {ws + L.dgates, 4 * H, U1 + 2 * H, 4 * H, G[GSCAN_P_DEC_WIH] + H, 3 * H, 4 * H, 2 * H};
+    gp[n++] = {ws + L.dgates, 4 * H, Hprev, 4 * H, G[GSCAN_P_DEC_WHH], H, 4 * H, H};
+    gp[n++] = {ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H};
+    gp[n++] = {ws + L.dqT, H, Hprev, 4 * H, G[GSCAN_P_TXT_QUERY_W], H, H, H};
+    gp[n++] = {ws + L.dqV, H, ws + L.Qp, H, G[GSCAN_P_VIS_QUERY_W], H, H, H};
+    if (d->conditional_attention) {
+      gp[n++] = {ws + L.dd, H, Hprev, 4 * H, G[GSCAN_P_COND_W], 2 * H, H, H};
+      gp[n++] = {ws + L.dd, H, U1 + 2 * H, 4 * H, G[GSCAN_P_COND_W] + H, 2 * H, H, H};
+    }
+    TRY(launch_grad_group(gp, n, R, sms, st));
+  }
   TRY(launch_colsum(ws + L.dgates, 4 * H, R, 4 * H, G[GSCAN_P_DEC_BIH], st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_DEC_BHH], G[GSCAN_P_DEC_BIH], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
-  TRY(launch_grad_gemm(ws + L.dqT, H, Hprev, 4 * H, G[GSCAN_P_TXT_QUERY_W], H, H, H, R, sms, st));
-  TRY(launch_grad_gemm(ws + L.dqV, H, ws + L.Qp, H, G[GSCAN_P_VIS_QUERY_W], H, H, H, R, sms, st));
-  if (d->conditional_attention) {
-    TRY(launch_grad_gemm(ws + L.dd, H, Hprev, 4 * H, G[GSCAN_P_COND_W], 2 * H, H, H, R, sms, st));
-    TRY(launch_grad_gemm(ws + L.dd, H, U1 + 2 * H, 4 * H, G[GSCAN_P_COND_W] + H, 2 * H, H, H, R, sms, st));
-    TRY(launch_colsum(ws + L.dd, H, R, H, G[GSCAN_P_COND_B], st));
-  }
+  if (d->conditional_attention) TRY(launch_colsum(ws + L.dd, H, R, H, G[GSCAN_P_COND_B], st));
   // decoder embedding: dE = dU[:, :H] + dgates . W_ih[:, :H], then scatter by token
   TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.dU, 4 * H, R, H, 4 * H, 1, st));
   {
@@ -1030,13 +1056,16 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     TRY(launch_colsum(ws + L.dconv + d->F, D, B * M, d->F, G[GSCAN_P_CONV2_B], sv));
     TRY(launch_colsum(ws + L.dconv + 2 * d->F, D, B * M, d->F, G[GSCAN_P_CONV3_B], sv));
   }
-  // B7: textual keys and initial state (helper stream 1)
-  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, stx));
-  TRY(matmul_nn(ws + L.dKT, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.denc_out, H, Ti * B, H, H, 0, stx));
+  // B7: initial state and textual keys (helper stream 1).  What needs only dh0 goes first; the products on dK^T wait
+  // for the value path of helper stream 0.
   TRY(launch_tanh_bwd(ws + L.dh0, ws + L.h0, ws + L.dpre0, (long)B * H, stx));
   TRY(launch_grad_gemm(ws + L.dpre0, H, ws + L.h_enc, H, G[GSCAN_P_E2D_W], H, H, H, B, sms, stx));
   TRY(launch_colsum(ws + L.dpre0, H, B, H, G[GSCAN_P_E2D_B], stx));
   TRY(matmul_nn(ws + L.dpre0, H, P[GSCAN_P_E2D_W], H, ws + L.dh_enc, H, B, H, H, 0, stx));
+  const int RE = B * Ti;
+  TRYCUDA(cudaMemsetAsync(ws + L.denc_x, 0, sizeof(float) * (size_t)RE * E, stx));
+  if (wait_value_path) TRYCUDA(cudaStreamWaitEvent(stx, S->join_ev[0], 0));
+  TRY(matmul_nn(ws + L.dKT, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.denc_out, H, Ti * B, H, H, 0, stx));
   // B8: encoder BPTT
   EncP ep{};
   ep.B = B; ep.Ti = Ti; ep.H = H;
@@ -1052,16 +1081,12 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   ep.denc_out = ws + L.denc_out;
   ep.dh_enc = ws + L.dh_enc;
   TRY(launch_enc(*d, ep, true, stx));
-  const int RE = B * Ti;
   const int wih[2] = {GSCAN_P_ENC_WIH, GSCAN_P_ENC_WIH_R}, whh[2] = {GSCAN_P_ENC_WHH, GSCAN_P_ENC_WHH_R};
   const int bih[2] = {GSCAN_P_ENC_BIH, GSCAN_P_ENC_BIH_R}, bhh[2] = {GSCAN_P_ENC_BHH, GSCAN_P_ENC_BHH_R};
-  for (int i = 0; i < 2; ++i) {
-    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.enc_x, E, G[wih[i]], E, 4 * H, E, RE, sms, stx));
-    TRY(launch_grad_gemm(ws + L.dga[i], 4 * H, ws + L.hprev[i], H, G[whh[i]], H, 4 * H, H, RE, sms, stx));
-    TRY(launch_colsum(ws + L.dga[i], 4 * H, RE, 4 * H, G[bih[i]], stx));
-    TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, stx));
-    TRY(matmul_nn(ws + L.dga[i], 4 * H, P[wih[i]], E, ws + L.denc_x, E, RE, E, 4 * H, i, stx));
-  }
+  // embedding gradient first (it is what the rest of this chain waits for): both directions add into the zeroed
+  // denc_x through split-K atomics, so neither waits for the other and each fills 8x more CTAs than one K-pass
+  for (int i = 0; i < 2; ++i)
+    TRY(launch_gemm(ws + L.dga[i], 4 * H, 1, P[wih[i]], E, 1, ws + L.denc_x, E, RE, E, 4 * H, nullptr, nullptr, 0, 0, 8, stx));
   {
     TRYCUDA(cudaMemsetAsync(G[GSCAN_P_ENC_EMB], 0, sizeof(float) * (size_t)d->Vi * E, stx));
     int use_smem = ((size_t)d->Vi * E * sizeof(float) <= 48 * 1024);
@@ -1071,6 +1096,20 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
         use_smem);
     GSCAN_CHECK_LAUNCH();
   }
+  {
+    tc::GroupProblem gp[5];
+    int n = 0;
+    for (int i = 0; i < 2; ++i) {
+      gp[n++] = {ws + L.dga[i], 4 * H, ws + L.hprev[i], H, G[whh[i]], H, 4 * H, H};
+      gp[n++] = {ws + L.dga[i], 4 * H, ws + L.enc_x, E, G[wih[i]], E, 4 * H, E};
+    }
+    TRY(launch_grad_group(gp, n, RE, sms, stx));
+    for (int i = 0; i < 2; ++i) {
+      TRY(launch_colsum(ws + L.dga[i], 4 * H, RE, 4 * H, G[bih[i]], stx));
+      TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, stx));
+    }
+  }
+  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, stx));
   if (S) {
     TRY(join_side(S, 0, st));
     TRY(join_side(S, 1, st));
