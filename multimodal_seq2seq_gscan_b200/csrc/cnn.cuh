@@ -92,7 +92,10 @@ __global__ void __launch_bounds__(256) cnn_forward_kernel(CnnShape s, const floa
   }
   __syncthreads();
   const int CF = s.C * s.F;
-  for (int o = threadIdx.x; o < M * D; o += blockDim.x) {
+  // grid.y slices the outputs of the example (the gathers below are L2-latency chains: the more threads, the
+  // shorter each chain); the non-zero loop is unrolled by 4 with predicated loads so that 4 gathers are in flight.
+  // Terms outside the window enter as fmaf(0, 0, acc) = acc: the sum and its order are those of the plain loop.
+  for (int o = blockIdx.y * blockDim.x + threadIdx.x; o < M * D; o += gridDim.y * blockDim.x) {
     const int cell = o / D, n = o - cell * D;
     const int conv = n / s.F, f = n - conv * s.F;
     const int k = s.ksize(conv), p = k >> 1;
@@ -100,11 +103,19 @@ __global__ void __launch_bounds__(256) cnn_forward_kernel(CnnShape s, const floa
     const float* w = Wt + s.woff(conv) + f;
     float acc = __ldg((conv == 0 ? b1 : (conv == 1 ? b2 : b3)) + f);
     const int rbase = p - ro, cbase = p - co;
-    for (int z = 0; z < nnz; ++z) {
-      const int e = idx_s[z];
-      const int dr = (e & 255) + rbase, dc = ((e >> 8) & 255) + cbase;
-      if ((unsigned)dr < (unsigned)k && (unsigned)dc < (unsigned)k)
-        acc = fmaf(val_s[z], __ldg(w + (dr * k + dc) * CF + (e >> 16) * s.F), acc);
+    for (int z0 = 0; z0 < nnz; z0 += 4) {
+      float wv[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int z = z0 + u;
+        const int e = z < nnz ? idx_s[z] : 0;
+        const int dr = (e & 255) + rbase, dc = ((e >> 8) & 255) + cbase;
+        const bool in = z < nnz && (unsigned)dr < (unsigned)k && (unsigned)dc < (unsigned)k;
+        wv[u] = in ? __ldg(w + (dr * k + dc) * CF + (e >> 16) * s.F) : 0.f;
+        xv[u] = in ? val_s[z] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], wv[u], acc);
     }
     acc = fmaxf(acc, 0.f);
     long oi = (long)b * M * D + o;
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(256) cnn_wgrad_kernel(CnnShape s, const float*
   __syncthreads();
   const int nnz = count_s;
   if (nnz == 0) return;
-  for (int o = threadIdx.x; o < M * D; o += blockDim.x) {
+  for (int o = blockIdx.y * blockDim.x + threadIdx.x; o < M * D; o += gridDim.y * blockDim.x) {
     int cell = o / D, n = o - cell * D;
     int conv = n / s.F, f = n - conv * s.F;
     int k = s.ksize(conv), p = k >> 1;
@@ -149,8 +160,18 @@ __global__ void __launch_bounds__(256) cnn_wgrad_kernel(CnnShape s, const float*
     int dr = ri - ro + p, dc = ci - co + p;
     if (dr < 0 || dr >= k || dc < 0 || dc >= k) continue;
     float acc = 0.f;
-    for (int z = 0; z < nnz; ++z)
-      acc = fmaf(val_s[z], __ldg(dconv + (long)idx_s[z] * M * D + o), acc);
+    for (int z0 = 0; z0 < nnz; z0 += 4) {   // 4 gathers in flight; same sum, same order
+      float gv[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int z = z0 + u;
+        const bool in = z < nnz;
+        gv[u] = in ? __ldg(dconv + (long)idx_s[z] * M * D + o) : 0.f;
+        xv[u] = in ? val_s[z] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc = fmaf(xv[u], gv[u], acc);
+    }
     atomicAdd(dWt + s.woff(conv) + (long)((dr * k + dc) * s.C + ch) * s.F + f, acc);
   }
 }

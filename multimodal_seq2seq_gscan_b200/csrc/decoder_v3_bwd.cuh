@@ -649,58 +649,119 @@ struct ValueZP {
   float *ZV, *ZT;                    // [B*36][ldv], [Ti*B][ldt]
   int ldv, ldt;
 };
-constexpr int kZW = kM + kMaxTi;     // weights per step: 36 beta | up to 16 alpha (zero padded)
 
-// grid = (B, ceil(NC / 256)); thread = one column of X for one example, 52 accumulators
-__global__ void __launch_bounds__(256) attn_value_z_kernel(ValueZP p) {
-  extern __shared__ __align__(16) float zw_s[];   // [T][kZW]
+// grid = (B, ceil(NC/4 / 64)), 256 threads.  Thread = (column quad, weight group wg): lane = 8 column quads x 4
+// groups, group wg owns the weight quads {wg, wg+4, wg+8, wg+12} of the 13 (so <= 16 weights x 4 columns = 32 packed
+// accumulators): per step one 16-byte quad of X and <= 4 shared-memory weight quads feed 32 FFMA2.
+// X is a strided gather (one 1 KB row segment per step, rows B*ld floats apart), so the kernel is bound by how many
+// loads it keeps in flight: each group of 4 lanes streams its column quad through a private shared-memory ring with
+// cp.async, kZRing rounds (of 4 steps) ahead - no registers held by loads in flight and no block barrier in the loop.
+// (First versions: register loads 4 steps ahead, 117-128 us; the 58 MB of X cost ~10 us at HBM speed.)
+constexpr int kZRing = 8;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// QW = weight quads per lane group: 3 (48 weight slots: 36 beta + Ti <= 12 alpha) or 4 (64 slots, Ti <= 16); the
+// unused slots hold zeros, so the inner loop is branch-free and the same for every lane.  Steps are padded to a
+// multiple of 4 with zero weights AND zero X (a stale ring slot could hold a NaN).
+inline int value_z_qw(int Ti) { return Ti <= 12 ? 3 : 4; }
+inline size_t value_z_smem_bytes(int T, int Ti) {
+  const int Tp = (T + 3) & ~3;
+  return sizeof(float) * ((size_t)Tp * 16 * value_z_qw(Ti) + (size_t)kZRing * 4 * 64 * 4);
+}
+
+template <int QW>
+__global__ void __launch_bounds__(256, 2) attn_value_z_kernel(ValueZP p) {
+  constexpr int ZS = 16 * QW;                      // weight slots per step
+  extern __shared__ __align__(16) float zw_s[];   // [Tp][ZS] weights, then the ring [kZRing][4 steps][64 quads] float4
   const int b = blockIdx.x, B = p.B, T = p.T, Ti = p.Ti, H = p.H;
-  for (int i = threadIdx.x; i < T * kZW; i += blockDim.x) {
-    const int t = i / kZW, k = i - t * kZW;
-    float v = 0.f;
-    if (k < kM) v = __ldg(p.beta + ((size_t)t * B + b) * kM + k);
-    else if (k - kM < Ti) v = __ldg(p.alpha + ((size_t)t * B + b) * Ti + (k - kM));
-    zw_s[i] = v;
+  const int Tp = (T + 3) & ~3, nr = Tp / 4;
+  float4* ring = reinterpret_cast<float4*>(zw_s + (size_t)Tp * ZS);
+  const int wg = threadIdx.x & 3, ql = threadIdx.x >> 2;
+  const int c = 4 * (blockIdx.y * 64 + ql);   // first of the 4 columns
+  const bool active = c < p.NC;
+  const float* src = p.dgates;
+  size_t ld = 4 * (size_t)H;
+  if (active) {
+    if (c < 4 * H) { src = p.dgates + c; }
+    else if (c < 5 * H) { src = p.dpre + (c - 4 * H); ld = H; }
+    else { src = p.dd + (c - 5 * H); ld = H; }
+    src += (size_t)b * ld;
   }
-  __syncthreads();
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
-  if (c >= p.NC) return;
-  const float* src;
-  size_t ld;
-  if (c < 4 * H) { src = p.dgates + c; ld = 4 * (size_t)H; }
-  else if (c < 5 * H) { src = p.dpre + (c - 4 * H); ld = H; }
-  else { src = p.dd + (c - 5 * H); ld = H; }
-  src += (size_t)b * ld;
   const size_t step = (size_t)B * ld;
-  float acc[kZW];
+  // lane wg of a quad's 4 lanes fetches step 4r + wg of round r; all 4 lanes consume all 4 steps
+  auto issue = [&](int r) {
+    const int t = 4 * r + wg;
+    if (r < nr) {
+      float4* dst = &ring[((r % kZRing) * 4 + wg) * 64 + ql];
+      if (active && t < T) cp_async16(dst, src + (size_t)t * step);
+      else *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+  // the attention weights of this example go in first, as one more (oldest) cp.async group: a dependent
+  // load -> store loop here cost 30 us of exposed latency
+  for (int i = threadIdx.x; i < Tp * ZS; i += blockDim.x) {
+    const int t = i / ZS, k = i - t * ZS;
+    if (t < T && k < kM) cp_async4(zw_s + i, p.beta + ((size_t)t * B + b) * kM + k);
+    else if (t < T && k - kM < Ti) cp_async4(zw_s + i, p.alpha + ((size_t)t * B + b) * Ti + (k - kM));
+    else zw_s[i] = 0.f;
+  }
+  cp_async_commit();
 #pragma unroll
-  for (int k = 0; k < kZW; ++k) acc[k] = 0.f;
-  for (int t0 = 0; t0 < T; t0 += 4) {
-    float x[4];
+  for (int r = 0; r < kZRing; ++r) issue(r);
+  cp_async_wait<kZRing>();
+  __syncthreads();
+  float2 acc[QW][4][2];                            // [owned quad][weight in quad][column pair]
 #pragma unroll
-    for (int u = 0; u < 4; ++u) x[u] = (t0 + u < T) ? __ldg(src + (size_t)(t0 + u) * step) : 0.f;
+  for (int q = 0; q < QW; ++q)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[q][k][0] = acc[q][k][1] = make_float2(0.f, 0.f);
+  for (int r = 0; r < nr; ++r) {
+    cp_async_wait<kZRing - 1>();
+    __syncwarp();
+    const float4* xr = ring + ((r % kZRing) * 4) * 64 + ql;
+    const float4* wr = reinterpret_cast<const float4*>(zw_s + (size_t)(4 * r) * ZS) + wg;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (t0 + u < T) {
-        const float4* w = reinterpret_cast<const float4*>(zw_s + (t0 + u) * kZW);
+      const float4 x = xr[u * 64];
+      const float2 x01 = make_float2(x.x, x.y), x23 = make_float2(x.z, x.w);
 #pragma unroll
-        for (int q = 0; q < kZW / 4; ++q) {
-          const float4 wv = w[q];
-          acc[4 * q] = fmaf(wv.x, x[u], acc[4 * q]);
-          acc[4 * q + 1] = fmaf(wv.y, x[u], acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(wv.z, x[u], acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(wv.w, x[u], acc[4 * q + 3]);
+      for (int q = 0; q < QW; ++q) {
+        const float4 wv = wr[u * (ZS / 4) + 4 * q];
+        const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 ww = make_float2(ws[k], ws[k]);
+          fma2(acc[q][k][0], ww, x01);
+          fma2(acc[q][k][1], ww, x23);
         }
       }
     }
+    __syncwarp();
+    issue(r + kZRing);
   }
-  if (c < p.ldv) {
+  if (!active) return;
 #pragma unroll
-    for (int m = 0; m < kM; ++m) p.ZV[((size_t)b * kM + m) * p.ldv + c] = acc[m];
+  for (int q = 0; q < QW; ++q) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int widx = 4 * (wg + 4 * q) + k;     // 0..35 beta, 36.. alpha
+      const float4 o = make_float4(acc[q][k][0].x, acc[q][k][0].y, acc[q][k][1].x, acc[q][k][1].y);
+      if (widx < kM) {
+        if (c < p.ldv) *reinterpret_cast<float4*>(p.ZV + ((size_t)b * kM + widx) * p.ldv + c) = o;
+      } else if (widx - kM < Ti) {
+        *reinterpret_cast<float4*>(p.ZT + ((size_t)(widx - kM) * B + b) * p.ldt + c) = o;
+      }
+    }
   }
-#pragma unroll
-  for (int j = 0; j < kMaxTi; ++j)
-    if (j < Ti) p.ZT[((size_t)j * B + b) * p.ldt + c] = acc[kM + j];
 }
 
 // Wst_V [5H][H] = [W_ih[:, 2H:3H] ; W_o2h[:, 3H:4H]],  Wst_T [6H][H] = [W_ih[:, H:2H] ; W_o2h[:, 2H:3H] ; W_c[:, H:2H]]

@@ -591,6 +591,20 @@ inline int num_sms() {
   return n;
 }
 
+// SM budget of the persistent kernels.  One CTA of this kernel takes a whole SM (197 KB of shared memory), and a
+// persistent wave never gives it back: while a GEMM holds all SMs, the small kernels of concurrent streams wait for
+// its end.  Callers that have latency-critical chains running beside a GEMM cap its grid for the scope of the launch.
+inline int& sm_cap() { static thread_local int cap = 0; return cap; }
+struct ScopedSmCap {
+  int prev;
+  explicit ScopedSmCap(int cap) : prev(sm_cap()) { sm_cap() = cap; }
+  ~ScopedSmCap() { sm_cap() = prev; }
+};
+inline int usable_sms() {
+  const int n = num_sms(), cap = sm_cap();
+  return (cap > 0 && cap < n) ? cap : n;
+}
+
 template <bool AK, bool BKM>
 inline int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t st) {
   static bool configured = false;
@@ -624,7 +638,7 @@ inline int launch(const float* A, long a_rs, long a_cs, const float* B, long b_r
   p.kb_per = ceil_div(p.kb_total, ksplit);
   p.ksplit = ceil_div(p.kb_total, p.kb_per);
   const int tiles = ceil_div(N, BN) * ceil_div(M, BM) * p.ksplit;
-  dim3 grid(min(tiles, num_sms()));
+  dim3 grid(min(tiles, usable_sms()));
   if (ak && bk) return launch_t<true, true>(ta, tb, p, grid, st);
   if (ak && !bk) return launch_t<true, false>(ta, tb, p, grid, st);
   if (!ak && bk) return launch_t<false, true>(ta, tb, p, grid, st);
@@ -671,9 +685,8 @@ inline int launch_group_tn(const GroupProblem* probs, int n, int R, cudaStream_t
   gt.ng = n;
   Params p{nullptr, 0, 0, 0, R, nullptr, nullptr, 0, 0, 0, 0, 1, mc.layout, mc.sbo, mc.lbo, nullptr};
   p.kb_total = ceil_div(R, BK);
-  // one persistent wave; GSCAN_GROUP_SM_LIMIT leaves the other SMs to kernels of concurrent streams
-  static const int sm_limit = getenv("GSCAN_GROUP_SM_LIMIT") ? atoi(getenv("GSCAN_GROUP_SM_LIMIT")) : 0;
-  const int sms = (sm_limit > 0 && mn * 4 <= sm_limit) ? min(sm_limit, num_sms()) : num_sms();
+  // one persistent wave over the SM budget of the caller
+  const int sms = max(usable_sms(), mn);
   int ksplit = max(1, min(ceil_div(R, 4 * BK), sms / mn));
   p.kb_per = ceil_div(p.kb_total, ksplit);
   p.ksplit = ceil_div(p.kb_total, p.kb_per);

@@ -61,6 +61,33 @@ void prof_mark(int idx, cudaStream_t st) {
   g_stage_seen[idx] = true;
 }
 
+// ---- chain timeline (debug): GSCAN_CHAIN_TIMES=1 records an event at named points of ANY stream and prints, at
+// the end of the call, when each point was reached relative to the first one (what the three concurrent chains of a
+// call really do to each other cannot be read off a serialised ncu launch list) ---------------------------------
+struct ChainMark { const char* name; cudaEvent_t ev; };
+std::vector<ChainMark>& chain_marks() { static std::vector<ChainMark> v; return v; }
+bool chain_times_on() { static const bool on = getenv("GSCAN_CHAIN_TIMES") != nullptr; return on; }
+void chain_mark(const char* name, cudaStream_t st) {
+  if (!chain_times_on()) return;
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, st);
+  chain_marks().push_back({name, e});
+}
+void chain_report(const char* title) {
+  if (!chain_times_on() || chain_marks().empty()) return;
+  cudaDeviceSynchronize();
+  fprintf(stderr, "[chain] %s:", title);
+  for (auto& m : chain_marks()) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, chain_marks()[0].ev, m.ev);
+    fprintf(stderr, " %s=%.0f", m.name, ms * 1000.f);
+    }
+  fprintf(stderr, "\n");
+  for (auto& m : chain_marks()) cudaEventDestroy(m.ev);
+  chain_marks().clear();
+}
+
 // ---- internal fork / join ------------------------------------------------------------------
 // Independent chains of small kernels (CNN | command encoder | decoder prelude; after the reverse sweep:
 // decoder weight gradients | visual keys -> CNN | textual keys -> encoder) run on two helper streams that fork
@@ -316,6 +343,14 @@ int launch_enc(const gscan_dims& d, const EncP& p, bool bwd, cudaStream_t st) {
   return 0;
 }
 
+// SM budgets (tc::ScopedSmCap) of the persistent GEMMs that run beside latency-critical helper chains; 0 = no cap.
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+int cap_prelude() { static const int c = env_int("GSCAN_CAP_PRELUDE", 96); return c; }
+int cap_post() { static const int c = env_int("GSCAN_CAP_POST", 120); return c; }
+
 int check_common(const gscan_dims* d, const float* const* params) {
   if (!d || !params) return GSCAN_E_BADARG;
   TRY(gscan_check_dims(d));
@@ -347,7 +382,8 @@ int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* sit
   GSCAN_CHECK_LAUNCH();
   size_t smem = (size_t)cs.M() * cs.C * 8;
   if (smem > 48 * 1024) TRY(set_smem(cnn_forward_kernel, smem));
-  cnn_forward_kernel<<<d.B, 256, smem, st>>>(cs, situations, Wt, P[GSCAN_P_CONV1_B], P[GSCAN_P_CONV2_B],
+  const int ysplit = max(1, min(8, ceil_div(cs.M() * cs.D(), 3 * 256)));   // ~3 outputs per thread
+  cnn_forward_kernel<<<dim3(d.B, ysplit), 256, smem, st>>>(cs, situations, Wt, P[GSCAN_P_CONV1_B], P[GSCAN_P_CONV2_B],
                                              P[GSCAN_P_CONV3_B], drop_cnn, feat);
   GSCAN_CHECK_LAUNCH();
   return 0;
@@ -363,7 +399,9 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
   cudaStream_t sc = S ? S->s[0] : st;
   if (S) TRY(fork_side(S, 0, st));
   TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, sc));
+  chain_mark("s0:cnn", sc);
   if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, sc));
+  chain_mark("s0:KV", sc);
   // command embeddings and their input-gate pre-activations for both directions
   {
     long n = (long)B * Ti * E;
@@ -397,6 +435,7 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
   ep.enc_out = ws + L.enc_out;
   ep.h_enc = ws + L.h_enc;
   TRY(launch_enc(d, ep, false, st));
+  chain_mark("enc_fwd", st);
   if (need_keys) {
     TRY(linear(ws + L.enc_out, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.KT, H, Ti * B, H, H, nullptr, nullptr, 0, st));
     TRY(linear(ws + L.h_enc, H, P[GSCAN_P_E2D_W], H, ws + L.h0, H, B, H, H, P[GSCAN_P_E2D_B], nullptr, 1, st));
@@ -812,25 +851,33 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   const long long* tgts = reinterpret_cast<const long long*>(targets);
 
   prof_mark(0, st);
-  // decoder prelude (depends on targets and weights only) on helper stream 1, beside the encoder side
+  chain_mark("fwd_start", st);
+  // Encoder side (CNN | command encoder: long chains of small kernels) on the high-priority helper streams, issued
+  // first; the decoder prelude (depends on targets and weights only; one big capped GEMM) fills in on the caller's
+  // stream.  (The other way round the encoder chain queued behind the prelude GEMM: 213 us before the sweep.)
   SideStreams* S = side_streams();
-  cudaStream_t sp = S ? S->s[1] : st;
+  cudaStream_t se = S ? S->s[1] : st;
   if (S) TRY(fork_side(S, 1, st));
-  TRY(pack_decoder_weights(*d, P, ws, L, sp));
+  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, se));
+  TRY(pack_decoder_weights(*d, P, ws, L, st));
   // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
   {
     long n = (long)B * Tt * H;
-    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sp>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
                                                               4 * H, B, Tt, 1);
     GSCAN_CHECK_LAUNCH();
   }
   float* U1 = ws + L.U + (size_t)B * 4 * H;
   // input-gate pre-activations of every step at once: Xe = E . W_ih[:, :H]^T + b_ih + b_hh
-  TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, Tt * B, 4 * H, H, P[GSCAN_P_DEC_BIH],
-             P[GSCAN_P_DEC_BHH], 0, sp));
-  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, st));
-  prof_mark(1, st);
+  {
+    tc::ScopedSmCap cap(S ? cap_prelude() : 0);   // leave SMs to the CNN and the command encoder running beside it
+    TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, Tt * B, 4 * H, H, P[GSCAN_P_DEC_BIH],
+               P[GSCAN_P_DEC_BHH], 0, st));
+  }
+  chain_mark("m:prelude", st);
   if (S) TRY(join_side(S, 1, st));
+  prof_mark(1, st);
+  chain_mark("m:joined", st);
   DecFwdP p{};
   fill_dec_fwd_common(*d, P, ws, L, p);
   p.T = Tt;
@@ -866,6 +913,7 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
     TRY(launch_dec_fwd(*d, p, false, st));
   }
   prof_mark(3, st);
+  chain_mark("m:sweep_done", st);
   // output projection for all steps at once, then log-softmax
   TRY(linear(U1, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre, H, Tt * B, H, 4 * H, nullptr, nullptr, 0, st));
   {
@@ -882,6 +930,8 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
     TRYCUDA(cudaMemcpyAsync(aux_logp, ws + L.aux_logp, sizeof(float) * (size_t)B * M, cudaMemcpyDeviceToDevice, st));
   }
   prof_mark(4, st);
+  chain_mark("m:fwd_end", st);
+  chain_report("forward");
   return GSCAN_OK;
 }
 
@@ -908,12 +958,19 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
 
   // B1: log-softmax backward, hidden_to_output
   prof_mark(5, st);
-  {
+  const bool head_fused = V <= kHeadMaxV && H <= 128 && getenv("GSCAN_HEAD_UNFUSED") == nullptr;
+  if (head_fused) {
+    // log-softmax backward, dpre and the hidden_to_output weight gradient in one pass over the rows
+    TRYCUDA(cudaMemsetAsync(G[GSCAN_P_H2O_W], 0, sizeof(float) * (size_t)V * H, st));
+    head_bwd_fused_kernel<<<min(ceil_div(R, 8), 2 * sms), 256, 2 * sizeof(float) * (size_t)V * H, st>>>(
+        d_logp, ws + L.logp, ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.dpre, G[GSCAN_P_H2O_W]);
+    GSCAN_CHECK_LAUNCH();
+  } else {
     int blocks = min(ceil_div(R, 8), 8 * sms);
     logsoftmax_bwd_kernel<<<blocks, 256, 0, st>>>(d_logp, ws + L.logp, V, B, Tt, ws + L.dlogits);
     GSCAN_CHECK_LAUNCH();
+    TRY(matmul_nn(ws + L.dlogits, V, P[GSCAN_P_H2O_W], H, ws + L.dpre, H, R, H, V, 0, st));
   }
-  TRY(matmul_nn(ws + L.dlogits, V, P[GSCAN_P_H2O_W], H, ws + L.dpre, H, R, H, V, 0, st));
   // B2: output_to_hidden.  The two output-head weight gradients are not needed by the sweep: they are issued after
   // it, on helper stream 1 beside the other post-sweep chains.  (Running them on a helper stream BEFORE the sweep
   // delays the cluster launch of the sweep behind the persistent GEMM: measured 1.11 -> 1.45 ms for the sweep.)
@@ -964,6 +1021,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   bool wait_value_path = false;
   if (bwd_v3) {
     prof_mark(7, st);   // the sweep kernel alone; what follows counts as batched weight-gradient work
+    chain_mark("sweep_end", st);
     if (S) TRY(fork_side(S, 0, st));
     // value path of both attentions, outside the recurrence and summed over time first (decoder_v3_bwd.cuh):
     // Z = sum_t w_t (x) [dgates | dpre | dd], then dK += Z . Wst
@@ -979,16 +1037,25 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       zp.alpha = ws + L.alpha; zp.beta = ws + L.beta;
       zp.B = B; zp.T = Tt; zp.Ti = Ti; zp.H = H; zp.NC = NC;
       zp.ZV = ws + L.ZV; zp.ZT = ws + L.ZT; zp.ldv = 5 * H; zp.ldt = NC;
-      size_t smem = sizeof(float) * (size_t)Tt * v3::kZW;
-      if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel, smem));
-      v3::attn_value_z_kernel<<<dim3(B, ceil_div(NC, 256)), 256, smem, sv>>>(zp);
+      const size_t smem = v3::value_z_smem_bytes(Tt, Ti);
+      const dim3 zgrid(B, ceil_div(NC / 4, 64));
+      if (v3::value_z_qw(Ti) == 3) {
+        if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel<3>, smem));
+        v3::attn_value_z_kernel<3><<<zgrid, 256, smem, sv>>>(zp);
+      } else {
+        if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel<4>, smem));
+        v3::attn_value_z_kernel<4><<<zgrid, 256, smem, sv>>>(zp);
+      }
       GSCAN_CHECK_LAUNCH();
-      TRY(matmul_nn(ws + L.ZV, 5 * H, ws + L.WstV, H, ws + L.dKV, H, B * M, H, 5 * H, 1, sv));
-      TRY(matmul_nn(ws + L.ZT, NC, ws + L.WstT, H, ws + L.dKT, H, Ti * B, H, NC, 1, sv));
+      chain_mark("s0:Z", sv);
+      // split-K (atomic adds onto the key-path part the sweep stored): short K loops on more SMs
+      TRY(launch_gemm(ws + L.ZV, 5 * H, 1, ws + L.WstV, H, 1, ws + L.dKV, H, B * M, H, 5 * H, nullptr, nullptr, 0, 0, 2, sv));
+      TRY(launch_gemm(ws + L.ZT, NC, 1, ws + L.WstT, H, 1, ws + L.dKT, H, Ti * B, H, NC, nullptr, nullptr, 0, 0, 4, sv));
+      chain_mark("s0:value_path", sv);
     }
     // helper stream 1: the output-head weight gradients right after the sweep, then (after the value path) the text chain
     if (S) TRY(fork_side(S, 1, st));
-    TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
+    if (!head_fused) TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
     if (S) {
       TRYCUDA(cudaEventRecord(S->join_ev[0], sv));   // value path done: dK^T, dK^V complete
       wait_value_path = true;
@@ -1000,7 +1067,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       TRY(fork_side(S, 0, st));
       TRY(fork_side(S, 1, st));
     }
-    TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
+    if (!head_fused) TRY(launch_grad_gemm(ws + L.dlogits, V, ws + L.pre, H, G[GSCAN_P_H2O_W], H, V, H, R, sms, stx));
   }
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
@@ -1020,21 +1087,31 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       gp[n++] = {ws + L.dd, H, Hprev, 4 * H, G[GSCAN_P_COND_W], 2 * H, H, H};
       gp[n++] = {ws + L.dd, H, U1 + 2 * H, 4 * H, G[GSCAN_P_COND_W] + H, 2 * H, H, H};
     }
+    tc::ScopedSmCap cap(S ? cap_post() : 0);   // the helper chains (CNN, encoder) need SMs meanwhile
+    // everything downstream on both helper streams hangs off the value path: it gets the chip first
+    static const bool main_waits = env_int("GSCAN_MAIN_WAITS_VALUE", 1) != 0;
+    if (wait_value_path && main_waits) TRYCUDA(cudaStreamWaitEvent(st, S->join_ev[0], 0));
     TRY(launch_grad_group(gp, n, R, sms, st));
   }
+  chain_mark("m:group", st);
   TRY(launch_colsum(ws + L.dgates, 4 * H, R, 4 * H, G[GSCAN_P_DEC_BIH], st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_DEC_BHH], G[GSCAN_P_DEC_BIH], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
   if (d->conditional_attention) TRY(launch_colsum(ws + L.dd, H, R, H, G[GSCAN_P_COND_B], st));
   // decoder embedding: dE = dU[:, :H] + dgates . W_ih[:, :H], then scatter by token
-  TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.dU, 4 * H, R, H, 4 * H, 1, st));
+  {
+    tc::ScopedSmCap cap(S ? cap_post() : 0);
+    TRY(matmul_nn(ws + L.dgates, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.dU, 4 * H, R, H, 4 * H, 1, st));
+  }
   {
     TRYCUDA(cudaMemsetAsync(G[GSCAN_P_DEC_EMB], 0, sizeof(float) * (size_t)V * H, st));
-    int use_smem = ((size_t)V * H * sizeof(float) <= 48 * 1024);
-    int rpb = 64;
-    embed_bwd_kernel<<<ceil_div(R, rpb), 256, use_smem ? (size_t)V * H * sizeof(float) : 0, st>>>(
+    const size_t tab = (size_t)embed_bwd_groups(H, 256) * V * H * sizeof(float);
+    int use_smem = tab > 0 && tab <= 48 * 1024;
+    int rpb = 128;
+    embed_bwd_kernel<<<ceil_div(R, rpb), 256, use_smem ? tab : 0, st>>>(
         tgts, Tt, ws + L.dU, 4 * H, drop_dec, G[GSCAN_P_DEC_EMB], H, V, d->pad_idx_out, B, Tt, 1, rpb, use_smem);
     GSCAN_CHECK_LAUNCH();
   }
+  chain_mark("m:dE_embed", st);
   prof_mark(8, st);
   // B6: visual keys -> CNN (helper stream 0)
   TRY(launch_grad_gemm(ws + L.dKV, H, ws + L.feat, D, G[GSCAN_P_VIS_KEY_W], D, H, D, B * M, sms, sv));
@@ -1047,7 +1124,8 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     TRYCUDA(cudaMemsetAsync(ws + L.dWt_cnn, 0, sizeof(float) * cs.wtotal(), sv));
     size_t smem = (size_t)B * 8;
     if (smem > 48 * 1024) TRY(set_smem(cnn_wgrad_kernel, smem));
-    cnn_wgrad_kernel<<<M * d->C, 256, smem, sv>>>(cs, situations, ws + L.dconv, ws + L.dWt_cnn);
+    const int ysplit = max(1, min(4, ceil_div(M * D, 5 * 256)));
+    cnn_wgrad_kernel<<<dim3(M * d->C, ysplit), 256, smem, sv>>>(cs, situations, ws + L.dconv, ws + L.dWt_cnn);
     GSCAN_CHECK_LAUNCH();
     cnn_relayout_kernel<<<ceil_div(cs.wtotal(), 256), 256, 0, sv>>>(cs, G[GSCAN_P_CONV1_W], G[GSCAN_P_CONV2_W],
                                                                    G[GSCAN_P_CONV3_W], ws + L.dWt_cnn, 0);
@@ -1056,6 +1134,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     TRY(launch_colsum(ws + L.dconv + d->F, D, B * M, d->F, G[GSCAN_P_CONV2_B], sv));
     TRY(launch_colsum(ws + L.dconv + 2 * d->F, D, B * M, d->F, G[GSCAN_P_CONV3_B], sv));
   }
+  chain_mark("s0:kv_cnn", sv);
   // B7: initial state and textual keys (helper stream 1).  What needs only dh0 goes first; the products on dK^T wait
   // for the value path of helper stream 0.
   TRY(launch_tanh_bwd(ws + L.dh0, ws + L.h0, ws + L.dpre0, (long)B * H, stx));
@@ -1064,6 +1143,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   TRY(matmul_nn(ws + L.dpre0, H, P[GSCAN_P_E2D_W], H, ws + L.dh_enc, H, B, H, H, 0, stx));
   const int RE = B * Ti;
   TRYCUDA(cudaMemsetAsync(ws + L.denc_x, 0, sizeof(float) * (size_t)RE * E, stx));
+  chain_mark("s1:h2o_e2d", stx);
   if (wait_value_path) TRYCUDA(cudaStreamWaitEvent(stx, S->join_ev[0], 0));
   TRY(matmul_nn(ws + L.dKT, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.denc_out, H, Ti * B, H, H, 0, stx));
   // B8: encoder BPTT
@@ -1081,6 +1161,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   ep.denc_out = ws + L.denc_out;
   ep.dh_enc = ws + L.dh_enc;
   TRY(launch_enc(*d, ep, true, stx));
+  chain_mark("s1:enc_bwd", stx);
   const int wih[2] = {GSCAN_P_ENC_WIH, GSCAN_P_ENC_WIH_R}, whh[2] = {GSCAN_P_ENC_WHH, GSCAN_P_ENC_WHH_R};
   const int bih[2] = {GSCAN_P_ENC_BIH, GSCAN_P_ENC_BIH_R}, bhh[2] = {GSCAN_P_ENC_BHH, GSCAN_P_ENC_BHH_R};
   // embedding gradient first (it is what the rest of this chain waits for): both directions add into the zeroed
@@ -1089,9 +1170,10 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     TRY(launch_gemm(ws + L.dga[i], 4 * H, 1, P[wih[i]], E, 1, ws + L.denc_x, E, RE, E, 4 * H, nullptr, nullptr, 0, 0, 8, stx));
   {
     TRYCUDA(cudaMemsetAsync(G[GSCAN_P_ENC_EMB], 0, sizeof(float) * (size_t)d->Vi * E, stx));
-    int use_smem = ((size_t)d->Vi * E * sizeof(float) <= 48 * 1024);
+    const size_t tab = (size_t)embed_bwd_groups(E, 256) * d->Vi * E * sizeof(float);
+    int use_smem = tab > 0 && tab <= 48 * 1024;
     int rpb = 64;
-    embed_bwd_kernel<<<ceil_div(RE, rpb), 256, use_smem ? (size_t)d->Vi * E * sizeof(float) : 0, stx>>>(
+    embed_bwd_kernel<<<ceil_div(RE, rpb), 256, use_smem ? tab : 0, stx>>>(
         cmds, d->Ti_stride, ws + L.denc_x, E, drop_enc, G[GSCAN_P_ENC_EMB], E, d->Vi, d->pad_idx_in, B, Ti, 0, rpb,
         use_smem);
     GSCAN_CHECK_LAUNCH();
@@ -1110,11 +1192,14 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     }
   }
   TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, stx));
+  chain_mark("s1:enc_wgrad", stx);
   if (S) {
     TRY(join_side(S, 0, st));
     TRY(join_side(S, 1, st));
   }
   prof_mark(9, st);
+  chain_mark("joined", st);
+  chain_report("backward after the sweep");
   return GSCAN_OK;
 }
 

@@ -59,7 +59,12 @@ __global__ void embed_kernel(const long long* __restrict__ tokens, int tok_strid
 }
 
 // Embedding scatter-add: dW[tok][h] += mask * dX[row][h] for tok != pad.  dW zeroed by host.
-// Each CTA walks a chunk of rows, accumulating into shared memory when the table fits.
+// Each CTA walks a chunk of rows.  use_smem: thread (g, h) = (tid / Wd, tid % Wd) owns column h of a private copy g of
+// the table in shared memory ([groups][Vsz][Wd] floats) and walks the rows r0 + g, r0 + g + groups, ... with plain
+// read-modify-writes - no atomics inside the CTA (the first version issued one shared-memory atomic per element and
+// took 28 us for the decoder table); the copies are summed at the end and added to dW with one atomic per entry.
+__host__ __device__ inline int embed_bwd_groups(int Wd, int nthreads) { return Wd <= nthreads ? nthreads / Wd : 0; }
+
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ tokens, int tok_stride,
                                                         const float* __restrict__ dX, long ldx,
                                                         const float* __restrict__ mask, float* __restrict__ dW,
@@ -69,12 +74,46 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
   const long R = (long)B * T;
   long r0 = (long)blockIdx.x * rows_per_block;
   long r1 = min(R, r0 + rows_per_block);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   if (use_smem) {
-    for (int i = threadIdx.x; i < Vsz * Wd; i += blockDim.x) acc_s[i] = 0.f;
+    const int groups = embed_bwd_groups(Wd, blockDim.x);
+    for (int i = threadIdx.x; i < groups * Vsz * Wd; i += blockDim.x) acc_s[i] = 0.f;
     __syncthreads();
+    const int g = threadIdx.x / Wd, h = threadIdx.x - g * Wd;
+    if (g < groups) {
+      float* mine = acc_s + (size_t)g * Vsz * Wd + h;
+      for (long rb = r0 + g; rb < r1; rb += 4L * groups) {
+        long long tok[4];
+        float x[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {   // 4 rows in flight
+          const long r = rb + (long)u * groups;
+          tok[u] = pad;
+          x[u] = 0.f;
+          if (r < r1) {
+            const int b = r / T, t = r - (long)b * T;
+            tok[u] = tokens[(long)b * tok_stride + t];
+            if (tok[u] != pad) {
+              const long xrow = row_mode == 0 ? r : ((long)t * B + b);
+              x[u] = __ldg(dX + xrow * ldx + h);
+              if (mask) x[u] *= __ldg(mask + r * Wd + h);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (tok[u] != pad) mine[tok[u] * Wd] += x[u];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Vsz * Wd; i += blockDim.x) {
+      float v = 0.f;
+      for (int k = 0; k < groups; ++k) v += acc_s[(size_t)k * Vsz * Wd + i];
+      if (v != 0.f) atomicAdd(dW + i, v);
+    }
+    return;
   }
-  // one warp per row: the rows of a block are in flight together instead of one after the other
+  // table too large for shared memory: one warp per row, global atomics
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (long r = r0 + warp; r < r1; r += nwarps) {
     int b = r / T, t = r - (long)b * T;
     long long tok = tokens[(long)b * tok_stride + t];
@@ -83,15 +122,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
     for (int h = lane; h < Wd; h += 32) {
       float g = __ldg(dX + xrow * ldx + h);
       if (mask) g *= __ldg(mask + r * Wd + h);
-      if (use_smem) atomicAdd(acc_s + tok * Wd + h, g);
-      else atomicAdd(dW + tok * Wd + h, g);
-    }
-  }
-  if (use_smem) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < Vsz * Wd; i += blockDim.x) {
-      float v = acc_s[i];
-      if (v != 0.f) atomicAdd(dW + i, v);
+      atomicAdd(dW + tok * Wd + h, g);
     }
   }
 }
@@ -114,19 +145,42 @@ __global__ void __launch_bounds__(256) out_logsoftmax_kernel(const float* __rest
   for (long row = (long)blockIdx.x * (blockDim.x >> 5) + warp; row < R; row += (long)gridDim.x * (blockDim.x >> 5)) {
     const float* x = pre + row * H;
     float l[kMaxVPerLane];
-    float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < kMaxVPerLane; ++i) {
-      int v = lane + 32 * i;
-      l[i] = -INFINITY;
-      if (v < V) {
+    for (int i = 0; i < kMaxVPerLane; ++i) l[i] = -INFINITY;
+    if (H <= 128) {
+      // lanes split the hidden axis (coalesced row load, 4 values per lane); one butterfly sum per vocabulary entry.
+      // (One lane per entry walking all H terms left 23 of 32 lanes idle for V = 9: 34 us for the 24,200 rows.)
+      float xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = (lane + 32 * i < H) ? __ldg(x + lane + 32 * i) : 0.f;
+      for (int v = 0; v < V; ++v) {
         const float* w = w_s + v * (H + 1);
         float s = 0.f;
-        for (int h = 0; h < H; ++h) s = fmaf(__ldg(x + h), w[h], s);
-        l[i] = s;
-        mx = fmaxf(mx, s);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (lane + 32 * i < H) s = fmaf(xv[i], w[lane + 32 * i], s);
+        s = warp_sum(s);
+        if ((v & 31) == lane) {
+#pragma unroll
+          for (int i = 0; i < kMaxVPerLane; ++i)
+            if (i == (v >> 5)) l[i] = s;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kMaxVPerLane; ++i) {
+        int v = lane + 32 * i;
+        if (v < V) {
+          const float* w = w_s + v * (H + 1);
+          float s = 0.f;
+          for (int h = 0; h < H; ++h) s = fmaf(__ldg(x + h), w[h], s);
+          l[i] = s;
+        }
       }
     }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMaxVPerLane; ++i) mx = fmaxf(mx, l[i]);
     mx = warp_max(mx);
     float sum = 0.f;
 #pragma unroll
@@ -144,6 +198,65 @@ __global__ void __launch_bounds__(256) out_logsoftmax_kernel(const float* __rest
       }
     }
   }
+}
+
+// Output head backward in one pass over the rows (V <= kHeadMaxV, H <= 128), replacing logsoftmax_bwd_kernel + the
+// [R x V] . [V x H] product + the [V x R] . [R x H] weight-gradient product:
+//   dlogits[row] = dlogp - exp(logp) * sum_v dlogp           (lane v holds entry v)
+//   dpre[row]    = dlogits[row] . W_h2o                       (lanes split H; dlogits broadcast by shuffles)
+//   dW_h2o      += dlogits[row]^T (x) pre[row]                (per-warp register accumulators, one atomic per CTA entry)
+// dW must be zeroed by the host.  dlogits is not materialised.
+constexpr int kHeadMaxV = 16;
+__global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __restrict__ dlogp, const float* __restrict__ logp,
+                                                             const float* __restrict__ pre, const float* __restrict__ Wh2o,
+                                                             int H, int V, int B, int T, float* __restrict__ dpre,
+                                                             float* __restrict__ dW) {
+  extern __shared__ __align__(16) float hb_s[];   // W [V][H] then dW accumulator [V][H]
+  float* w_s = hb_s;
+  float* acc_s = hb_s + V * H;
+  for (int i = threadIdx.x; i < V * H; i += blockDim.x) { w_s[i] = __ldg(Wh2o + i); acc_s[i] = 0.f; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long R = (long)B * T;
+  float acc[kHeadMaxV][4];
+#pragma unroll
+  for (int v = 0; v < kHeadMaxV; ++v)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[v][i] = 0.f;
+  for (long row = (long)blockIdx.x * (blockDim.x >> 5) + warp; row < R; row += (long)gridDim.x * (blockDim.x >> 5)) {
+    const int t = row / B, b = row - (long)t * B;
+    const long off = ((long)b * T + t) * V;
+    const float dl = lane < V ? __ldg(dlogp + off + lane) : 0.f;
+    const float lp = lane < V ? __ldg(logp + off + lane) : 0.f;
+    float xv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xv[i] = (lane + 32 * i < H) ? __ldg(pre + row * H + lane + 32 * i) : 0.f;
+    const float s = warp_sum(dl);
+    const float dlog = lane < V ? dl - expf(lp) * s : 0.f;
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int v = 0; v < kHeadMaxV; ++v) {
+      if (v < V) {
+        const float dv = __shfl_sync(0xffffffffu, dlog, v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (lane + 32 * i < H) d[i] = fmaf(dv, w_s[v * H + lane + 32 * i], d[i]);
+          acc[v][i] = fmaf(dv, xv[i], acc[v][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (lane + 32 * i < H) dpre[row * H + lane + 32 * i] = d[i];
+  }
+#pragma unroll
+  for (int v = 0; v < kHeadMaxV; ++v)
+    if (v < V)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (lane + 32 * i < H) atomicAdd(acc_s + v * H + lane + 32 * i, acc[v][i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < V * H; i += blockDim.x) atomicAdd(dW + i, acc_s[i]);
 }
 
 // dlogits[row][v] = dlogp[b][t][v] - exp(logp[b][t][v]) * sum_v dlogp[b][t][v]; row = t*B + b
