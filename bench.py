@@ -95,7 +95,8 @@ def read_peaks():
             p = json.load(f)
         out = dict(fallback, source="measured")
         for key in ("hbm_gbs", "bf16_tflops", "sm_max_mhz"):
-            for cand in (key, key + "_sustained"):
+            # the sweep is timed inside a long step: the sustained figure is the one that applies, when the file has it
+            for cand in (key + "_sustained", key):
                 if cand in p:
                     out[key] = number(p[cand])
                     break

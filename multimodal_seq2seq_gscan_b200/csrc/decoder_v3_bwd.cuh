@@ -75,6 +75,11 @@ struct DecBwd3P {
   float* dh0;               // [B][H]
   float *dvT, *dvV;         // [H] each, atomically accumulated (zeroed by the host)
   long long* timeline;
+  // progress signals: every CTA adds 1 to progress[k] once all its global stores of the steps t >= t_signal[k] are visible
+  // (the host lets work on those rows start in the shadow of the rest of the sweep: cuStreamWaitValue32)
+  unsigned int* progress;   // [n_signals] words, zeroed by the host
+  int n_signals;
+  int t_signal[4];          // descending
 };
 
 // o = W_tile[16 x 8*NSTEPS] . x^T: fp32 fragments from shared memory, split into tf32 hi/lo on the fly
@@ -546,7 +551,17 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
         if (an_ok) p.dqT[(row0 + an) * kH + S0 + ah] = dq;
       }
     }
+    // dq_T was the last global store of the step: publish "rows t >= t_signal are complete" (fence by every writer
+    // before the block barrier, one add per CTA after it)
+    int sig = -1;
+    if (p.progress != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < p.n_signals && t == p.t_signal[k]) sig = k;
+    }
+    if (sig >= 0) __threadfence();
     __syncthreads();
+    if (sig >= 0 && tid == 0) atomicAdd(p.progress + sig, 1u);
     GSCAN3_STAMP(14);
     // ---- B12: last piece of dh, W_qT^T dq_T, added to the earlier pieces and reduce-scattered (X_d) ------------------------------
     if (warp < kTiles) {

@@ -652,28 +652,51 @@ inline bool group_eligible(const GroupProblem& q, int R) { return eligible(q.X, 
 
 // All problems in ONE persistent launch (plus one launch that zeroes the destinations).  The tensor maps are
 // rebuilt only when a pointer or shape changed since the previous call (the workspace is stable across steps).
-inline int launch_group_tn(const GroupProblem* probs, int n, int R, cudaStream_t st) {
+inline int launch_group_zero(const GroupProblem* probs, int n, cudaStream_t st) {
   if (n <= 0) return 0;
   if (n > MAXG) return -3;
-  struct Cache { GroupProblem key[MAXG]; int n = 0, R = 0; GroupMaps maps; };
-  static thread_local Cache cache;
+  GroupTable gt{};
+  for (int g = 0; g < n; ++g) { gt.C[g] = probs[g].C; gt.ldc[g] = probs[g].ldc; gt.M[g] = probs[g].N1; gt.N[g] = probs[g].N2; }
+  gt.ng = n;
+  group_zero_kernel<<<dim3(16, n), 256, 0, st>>>(gt);
+  GSCAN_CHECK_LAUNCH();
+  return 0;
+}
+
+// zero_first: zero the destinations here (else the caller did, e.g. before two partial launches over row ranges);
+// ksplit_hint > 0 fixes the number of K-splits (default: one persistent wave over the SM budget).
+inline int launch_group_tn(const GroupProblem* probs, int n, int R, cudaStream_t st, bool zero_first = true,
+                           int ksplit_hint = 0) {
+  if (n <= 0) return 0;
+  if (n > MAXG) return -3;
+  struct Entry { GroupProblem key[MAXG]; int n = 0, R = 0; GroupMaps maps; };
+  struct Cache { Entry e[8]; int next = 0; };
+  static thread_local Cache store;
   const MnConfig& mc = mn_config();
   const CUtensorMapSwizzle mn_swz = (CUtensorMapSwizzle)mc.tma_swizzle;
-  bool same = cache.n == n && cache.R == R;
-  for (int g = 0; same && g < n; ++g) same = memcmp(&cache.key[g], &probs[g], sizeof(GroupProblem)) == 0;
-  if (!same) {
-    cache.n = 0;
-    for (int g = 0; g < n; ++g) {
-      int rc = make_map(&cache.maps.a[g], probs[g].X, probs[g].N1, R, probs[g].ldx, BK, mn_swz);
-      if (rc) return rc;
-      rc = make_map(&cache.maps.b[g], probs[g].Y, probs[g].N2, R, probs[g].ldy, BK, mn_swz);
-      if (rc) return rc;
-      memset(&cache.key[g], 0, sizeof(GroupProblem));
-      cache.key[g] = probs[g];
-    }
-    cache.n = n;
-    cache.R = R;
+  Entry* hit = nullptr;
+  for (auto& e : store.e) {
+    bool same = e.n == n && e.R == R;
+    for (int g = 0; same && g < n; ++g) same = memcmp(&e.key[g], &probs[g], sizeof(GroupProblem)) == 0;
+    if (same) { hit = &e; break; }
   }
+  if (!hit) {
+    Entry& e = store.e[store.next];
+    store.next = (store.next + 1) % 8;
+    e.n = 0;
+    for (int g = 0; g < n; ++g) {
+      int rc = make_map(&e.maps.a[g], probs[g].X, probs[g].N1, R, probs[g].ldx, BK, mn_swz);
+      if (rc) return rc;
+      rc = make_map(&e.maps.b[g], probs[g].Y, probs[g].N2, R, probs[g].ldy, BK, mn_swz);
+      if (rc) return rc;
+      memset(&e.key[g], 0, sizeof(GroupProblem));
+      e.key[g] = probs[g];
+    }
+    e.n = n;
+    e.R = R;
+    hit = &e;
+  }
+  Entry& cache = *hit;
   GroupTable gt{};
   int mn = 0;
   for (int g = 0; g < n; ++g) {
@@ -686,13 +709,21 @@ inline int launch_group_tn(const GroupProblem* probs, int n, int R, cudaStream_t
   Params p{nullptr, 0, 0, 0, R, nullptr, nullptr, 0, 0, 0, 0, 1, mc.layout, mc.sbo, mc.lbo, nullptr};
   p.kb_total = ceil_div(R, BK);
   // one persistent wave over the SM budget of the caller
-  const int sms = max(usable_sms(), mn);
+  const int sms = ksplit_hint > 0 ? usable_sms() : max(usable_sms(), mn);
   int ksplit = max(1, min(ceil_div(R, 4 * BK), sms / mn));
+  if (ksplit_hint > 0) ksplit = min(ksplit_hint, ceil_div(R, 4 * BK));
   p.kb_per = ceil_div(p.kb_total, ksplit);
   p.ksplit = ceil_div(p.kb_total, p.kb_per);
-  group_zero_kernel<<<dim3(16, n), 256, 0, st>>>(gt);
-  GSCAN_CHECK_LAUNCH();
-  if (p.ksplit == 1) p.accumulate = 0;
+  if (!zero_first && p.ksplit == 1 && p.kb_total >= 2) {   // partial launches may overlap in time: atomics only
+    p.kb_per = ceil_div(p.kb_total, 2);
+    p.ksplit = ceil_div(p.kb_total, p.kb_per);
+  }
+  if (zero_first) {
+    group_zero_kernel<<<dim3(16, n), 256, 0, st>>>(gt);
+    GSCAN_CHECK_LAUNCH();
+  } else if (p.ksplit == 1) {
+    p.accumulate = 1;   // destinations hold the other partial sums
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_group_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);

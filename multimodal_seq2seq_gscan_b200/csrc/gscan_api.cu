@@ -94,8 +94,8 @@ void chain_report(const char* title) {
 // from and join back into the caller's stream through events, so the caller still sees plain stream semantics:
 // everything a call enqueues completes before anything the caller enqueues on `stream` afterwards.
 struct SideStreams {
-  cudaStream_t s[2] = {nullptr, nullptr};
-  cudaEvent_t fork_ev[2] = {nullptr, nullptr}, join_ev[2] = {nullptr, nullptr};
+  cudaStream_t s[3] = {nullptr, nullptr, nullptr};   // [0], [1]: high priority chains; [2]: shadow work, lowest priority
+  cudaEvent_t fork_ev[3] = {nullptr, nullptr, nullptr}, join_ev[3] = {nullptr, nullptr, nullptr};
   bool ok = false;
 };
 SideStreams* side_streams() {
@@ -104,12 +104,12 @@ SideStreams* side_streams() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
   SideStreams& S = per_device[dev];
   if (!S.ok) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       // highest priority: the helper chains are long sequences of small kernels, and their CTAs must not queue
       // behind the persistent GEMMs of the caller's stream whenever an SM has room for them
       int prio_lo = 0, prio_hi = 0;
-      if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_hi = 0;
-      if (cudaStreamCreateWithPriority(&S.s[i], cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
+      if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) prio_lo = prio_hi = 0;
+      if (cudaStreamCreateWithPriority(&S.s[i], cudaStreamNonBlocking, i < 2 ? prio_hi : prio_lo) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&S.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&S.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
@@ -146,6 +146,7 @@ struct Layout {
   // backward scratch
   size_t dlogits, dpre, dU, dgates, dd, dqV, dqT, dKT, dKV, dh0, dbeta_aux, dfeat, dconv, dWt_cnn;
   size_t denc_out, dh_enc, dpre0, dga[2], hprev[2], denc_x, dvec;
+  size_t progress;             // sweep progress word (shadow scheduling of the weight-gradient GEMM)
   size_t ZV, ZT, WstV, WstT;   // reordered value path of the attentions (v3::attn_value_z_kernel)
   int RA, RB;
 };
@@ -205,6 +206,7 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
     L.dfeat = L.take(B * M * D);
     L.dconv = L.take(B * M * D);
     L.dWt_cnn = L.take(cs.wtotal());
+    L.progress = L.take(4);
     L.ZV = L.take(B * M * 5 * H);
     L.ZT = L.take(Ti * B * 6 * H);
     L.WstV = L.take(5 * H * H);
@@ -343,6 +345,22 @@ int launch_enc(const gscan_dims& d, const EncP& p, bool bwd, cudaStream_t st) {
   return 0;
 }
 
+// cuStreamWaitValue32 through the runtime's driver entry point table (no libcuda link dependency)
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn stream_wait_value_fn() {
+  static StreamWaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<StreamWaitValue32Fn>(ptr);
+  }
+  return fn;
+}
+
 // SM budgets (tc::ScopedSmCap) of the persistent GEMMs that run beside latency-critical helper chains; 0 = no cap.
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -390,18 +408,21 @@ int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* sit
 }
 
 // CNN + visual keys + encoder + textual keys + initial decoder state, shared by forward / encode / greedy.
+// The encoder chain runs on `st`.  The CNN chain runs on `cnn_stream` when the caller passes one (and then orders it
+// itself), else on helper stream 0, forked from and joined back into `st` here.
 int run_encoder_side(const gscan_dims& d, const float* const* P, const long long* commands, const int* cmd_len,
                      const float* situations, const float* drop_cnn, const float* drop_enc, float* ws,
-                     const Layout& L, bool need_keys, cudaStream_t st) {
+                     const Layout& L, bool need_keys, cudaStream_t st, cudaStream_t cnn_stream = nullptr,
+                     bool cnn_stream_given = false) {
   const int B = d.B, Ti = d.Ti, M = d.G * d.G, D = 3 * d.F, H = d.H, E = d.E;
-  // the situation CNN (+ visual keys) is independent of the command encoder: helper stream 0
-  SideStreams* S = side_streams();
-  cudaStream_t sc = S ? S->s[0] : st;
+  // the situation CNN (+ visual keys) is independent of the command encoder
+  SideStreams* S = cnn_stream_given ? nullptr : side_streams();
+  cudaStream_t sc = cnn_stream_given ? cnn_stream : (S ? S->s[0] : st);
   if (S) TRY(fork_side(S, 0, st));
   TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, sc));
-  chain_mark("s0:cnn", sc);
+  chain_mark("cnn", sc);
   if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, sc));
-  chain_mark("s0:KV", sc);
+  chain_mark("KV", sc);
   // command embeddings and their input-gate pre-activations for both directions
   {
     long n = (long)B * Ti * E;
@@ -852,29 +873,35 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
 
   prof_mark(0, st);
   chain_mark("fwd_start", st);
-  // Encoder side (CNN | command encoder: long chains of small kernels) on the high-priority helper streams, issued
-  // first; the decoder prelude (depends on targets and weights only; one big capped GEMM) fills in on the caller's
-  // stream.  (The other way round the encoder chain queued behind the prelude GEMM: 213 us before the sweep.)
+  // Three chains before the sweep: the command encoder (a long chain of small kernels: high-priority helper stream 1,
+  // issued first), the decoder prelude (depends on targets and weights only; one big GEMM, capped: high-priority
+  // helper stream 0) and the situation CNN (wide kernels of small CTAs that co-reside with the GEMM's: the caller's
+  // stream, which fills whatever the other two leave).  Measured orders: prelude on a helper stream and encoder side
+  // on the caller's 213 us; encoder side on helper streams and prelude on the caller's 183 us.
   SideStreams* S = side_streams();
-  cudaStream_t se = S ? S->s[1] : st;
-  if (S) TRY(fork_side(S, 1, st));
-  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, se));
-  TRY(pack_decoder_weights(*d, P, ws, L, st));
+  cudaStream_t se = S ? S->s[1] : st, sp = S ? S->s[0] : st;
+  if (S) {
+    TRY(fork_side(S, 1, st));
+    TRY(fork_side(S, 0, st));
+  }
+  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, se, st, true));
+  TRY(pack_decoder_weights(*d, P, ws, L, sp));
   // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
   {
     long n = (long)B * Tt * H;
-    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
+    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sp>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
                                                               4 * H, B, Tt, 1);
     GSCAN_CHECK_LAUNCH();
   }
   float* U1 = ws + L.U + (size_t)B * 4 * H;
   // input-gate pre-activations of every step at once: Xe = E . W_ih[:, :H]^T + b_ih + b_hh
   {
-    tc::ScopedSmCap cap(S ? cap_prelude() : 0);   // leave SMs to the CNN and the command encoder running beside it
+    tc::ScopedSmCap cap(S ? cap_prelude() : 0);   // leave SMs to the command encoder running beside it
     TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, Tt * B, 4 * H, H, P[GSCAN_P_DEC_BIH],
-               P[GSCAN_P_DEC_BHH], 0, st));
+               P[GSCAN_P_DEC_BHH], 0, sp));
   }
-  chain_mark("m:prelude", st);
+  chain_mark("s0:prelude", sp);
+  if (S) TRY(join_side(S, 0, st));
   if (S) TRY(join_side(S, 1, st));
   prof_mark(1, st);
   chain_mark("m:joined", st);
@@ -997,10 +1024,65 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   bp.dgates = ws + L.dgates; bp.dd = ws + L.dd; bp.dqV = ws + L.dqV; bp.dqT = ws + L.dqT;
   bp.dKT = ws + L.dKT; bp.dKV = ws + L.dKV; bp.dh0 = ws + L.dh0;
   bp.dvT = ws + L.dvec; bp.dvV = ws + L.dvec + H;
+  // decoder weight gradients (and the output_to_hidden one) as "TN" products over all R = Tt*B rows, one grouped
+  // tcgen05 launch; the list is needed before the sweep for the shadow schedule below
+  const float* Hprev = U0 + H;       // rows t*B+b hold h_{t-1}
+  tc::GroupProblem gp[tc::MAXG];
+  int ngp = 0;
+  gp[ngp++] = {ws + L.dgates, 4 * H, U1, 4 * H, G[GSCAN_P_DEC_WIH], 3 * H, 4 * H, H};
+  gp[ngp++] = {ws + L.dgates, 4 * H, U1 + 2 * H, 4 * H, G[GSCAN_P_DEC_WIH] + H, 3 * H, 4 * H, 2 * H};
+  gp[ngp++] = {ws + L.dgates, 4 * H, Hprev, 4 * H, G[GSCAN_P_DEC_WHH], H, 4 * H, H};
+  gp[ngp++] = {ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H};
+  gp[ngp++] = {ws + L.dqT, H, Hprev, 4 * H, G[GSCAN_P_TXT_QUERY_W], H, H, H};
+  gp[ngp++] = {ws + L.dqV, H, ws + L.Qp, H, G[GSCAN_P_VIS_QUERY_W], H, H, H};
+  if (d->conditional_attention) {
+    gp[ngp++] = {ws + L.dd, H, Hprev, 4 * H, G[GSCAN_P_COND_W], 2 * H, H, H};
+    gp[ngp++] = {ws + L.dd, H, U1 + 2 * H, 4 * H, G[GSCAN_P_COND_W] + H, 2 * H, H, H};
+  }
+  // Shadow schedule: the sweep occupies 125 of the 148 SMs for ~1.1 ms and produces the rows of the GEMM operands
+  // from the last step backwards.  Once every CTA has published the rows t >= t_sig (a counter in the workspace,
+  // awaited by helper stream 2 through cuStreamWaitValue32) the grouped weight-gradient GEMM over THOSE rows runs on
+  // the idle SMs beside the rest of the sweep; only the rows t < t_sig are left for after it.  Both partial launches
+  // add into the destinations (zeroed before the sweep) with split-K atomics.
+  const int sweep_ctas = ceil_div(B, v3::kNB) * v3::kC;
+  const int idle_sms = sms - sweep_ctas;
+  // cut points in percent of Tt, descending: chunk k = steps [cut_k, cut_{k-1}) is launched at signal k.  Measured at
+  // B = 200: one signal at 45 % ends 24 us before the sweep does; three signals put 85 % of the rows into the shadow.
+  int t_cut[4];
+  int n_cut = 0;
+  {
+    const char* spec = getenv("GSCAN_SHADOW_CUTS");
+    if (!spec) spec = "70,40,15";
+    int prev = Tt;
+    for (const char* q = spec; *q && n_cut < 4;) {
+      const int pct = atoi(q);
+      const int t = pct * Tt / 100;
+      if (pct > 0 && pct < 100 && t > 0 && t < prev) { t_cut[n_cut++] = t; prev = t; }
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+  }
+  bool shadow = S && v3_bwd_shape_ok(*d) && stream_wait_value_fn() && env_int("GSCAN_SHADOW", 1) != 0 && Tt >= 16 &&
+                idle_sms >= 8 && n_cut > 0;
+  for (int k = 0; shadow && k <= n_cut; ++k) {   // every chunk, and what is left for after the sweep, must take the tcgen05 path
+    const int rows = ((k == 0 ? Tt : t_cut[k - 1]) - (k == n_cut ? 0 : t_cut[k])) * B;
+    for (int i = 0; shadow && i < ngp; ++i) shadow = rows >= 1024 && tc::group_eligible(gp[i], rows);
+  }
+  unsigned int* progress = reinterpret_cast<unsigned int*>(ws + L.progress);
+  if (shadow) {
+    TRYCUDA(cudaMemsetAsync(progress, 0, 4 * sizeof(unsigned int), st));
+    TRY(tc::launch_group_zero(gp, ngp, st));
+    TRY(fork_side(S, 2, st));   // helper stream 2 starts from here, NOT from the end of the sweep
+  }
   prof_mark(6, st);
   bool bwd_v3 = false;
   if (v3_bwd_shape_ok(*d)) {
     v3::DecBwd3P b3{};
+    if (shadow) {
+      b3.progress = progress;
+      b3.n_signals = n_cut;
+      for (int k = 0; k < n_cut; ++k) b3.t_signal[k] = t_cut[k];
+    }
     b3.B = B; b3.T = Tt; b3.Ti = Ti;
     b3.W_ih = bp.W_ih; b3.W_hh = bp.W_hh; b3.W_qV = bp.W_qV; b3.W_c = bp.W_c; b3.W_qT = bp.W_qT;
     b3.PT = ws + L.PT;   // computed by the forward call on this workspace
@@ -1012,6 +1094,29 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     int rc = launch_dec_bwd_v3(*d, b3, st);
     if (rc == 0) bwd_v3 = true;
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
+    if (shadow && !bwd_v3) {      // nobody will signal: undo (the zeroing is harmless)
+      shadow = false;
+      TRY(join_side(S, 2, st));
+    }
+    if (shadow) {
+      cudaStream_t sh = S->s[2];
+      tc::ScopedSmCap cap(idle_sms);
+      for (int k = 0; k < n_cut; ++k) {
+        if (stream_wait_value_fn()((CUstream)sh, (CUdeviceptr)(progress + k), (cuuint32_t)sweep_ctas, 0u /* GEQ */) !=
+            CUDA_SUCCESS)
+          return GSCAN_E_UNSUPPORTED;
+        const int t0 = t_cut[k], t1 = k == 0 ? Tt : t_cut[k - 1];
+        tc::GroupProblem part[tc::MAXG];
+        const size_t r0 = (size_t)t0 * B;
+        for (int i = 0; i < ngp; ++i) {
+          part[i] = gp[i];
+          part[i].X += r0 * gp[i].ldx;
+          part[i].Y += r0 * gp[i].ldy;
+        }
+        TRY(tc::launch_group_tn(part, ngp, (t1 - t0) * B, sh, false, idle_sms));   // units = tiles x idle SMs: even rounds
+      }
+      chain_mark("s2:shadow_group", sh);
+    }
   }
   // Three independent chains from here, joined before returning:
   //   caller's stream  decoder weight gradients, decoder embedding
@@ -1071,27 +1176,14 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   }
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
-  // B5: decoder weight gradients (and the output_to_hidden one) as "TN" products over all R = Tt*B rows: ONE grouped
-  // tcgen05 launch (24 output tiles x 6 K-splits = one wave of 144 CTAs) instead of nine split-K launches
-  const float* Hprev = U0 + H;       // rows t*B+b hold h_{t-1}
+  // B5: decoder weight gradients: what the shadow launch left (rows t < t_sig), or everything
   {
-    tc::GroupProblem gp[tc::MAXG];
-    int n = 0;
-    gp[n++] = {ws + L.dgates, 4 * H, U1, 4 * H, G[GSCAN_P_DEC_WIH], 3 * H, 4 * H, H};
-    gp[n++] = {ws + L.dgates, 4 * H, U1 + 2 * H, 4 * H, G[GSCAN_P_DEC_WIH] + H, 3 * H, 4 * H, 2 * H};
-    gp[n++] = {ws + L.dgates, 4 * H, Hprev, 4 * H, G[GSCAN_P_DEC_WHH], H, 4 * H, H};
-    gp[n++] = {ws + L.dpre, H, U1, 4 * H, G[GSCAN_P_O2H_W], 4 * H, H, 4 * H};
-    gp[n++] = {ws + L.dqT, H, Hprev, 4 * H, G[GSCAN_P_TXT_QUERY_W], H, H, H};
-    gp[n++] = {ws + L.dqV, H, ws + L.Qp, H, G[GSCAN_P_VIS_QUERY_W], H, H, H};
-    if (d->conditional_attention) {
-      gp[n++] = {ws + L.dd, H, Hprev, 4 * H, G[GSCAN_P_COND_W], 2 * H, H, H};
-      gp[n++] = {ws + L.dd, H, U1 + 2 * H, 4 * H, G[GSCAN_P_COND_W] + H, 2 * H, H, H};
-    }
     tc::ScopedSmCap cap(S ? cap_post() : 0);   // the helper chains (CNN, encoder) need SMs meanwhile
     // everything downstream on both helper streams hangs off the value path: it gets the chip first
     static const bool main_waits = env_int("GSCAN_MAIN_WAITS_VALUE", 1) != 0;
     if (wait_value_path && main_waits) TRYCUDA(cudaStreamWaitEvent(st, S->join_ev[0], 0));
-    TRY(launch_grad_group(gp, n, R, sms, st));
+    if (shadow) TRY(tc::launch_group_tn(gp, ngp, t_cut[n_cut - 1] * B, st, false, 0));
+    else TRY(launch_grad_group(gp, ngp, R, sms, st));
   }
   chain_mark("m:group", st);
   TRY(launch_colsum(ws + L.dgates, 4 * H, R, 4 * H, G[GSCAN_P_DEC_BIH], st));
@@ -1106,7 +1198,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     TRYCUDA(cudaMemsetAsync(G[GSCAN_P_DEC_EMB], 0, sizeof(float) * (size_t)V * H, st));
     const size_t tab = (size_t)embed_bwd_groups(H, 256) * V * H * sizeof(float);
     int use_smem = tab > 0 && tab <= 48 * 1024;
-    int rpb = 128;
+    int rpb = 64;
     embed_bwd_kernel<<<ceil_div(R, rpb), 256, use_smem ? tab : 0, st>>>(
         tgts, Tt, ws + L.dU, 4 * H, drop_dec, G[GSCAN_P_DEC_EMB], H, V, d->pad_idx_out, B, Tt, 1, rpb, use_smem);
     GSCAN_CHECK_LAUNCH();
@@ -1196,6 +1288,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   if (S) {
     TRY(join_side(S, 0, st));
     TRY(join_side(S, 1, st));
+    if (shadow) TRY(join_side(S, 2, st));
   }
   prof_mark(9, st);
   chain_mark("joined", st);

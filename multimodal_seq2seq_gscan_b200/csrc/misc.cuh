@@ -81,11 +81,12 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
     const int g = threadIdx.x / Wd, h = threadIdx.x - g * Wd;
     if (g < groups) {
       float* mine = acc_s + (size_t)g * Vsz * Wd + h;
-      for (long rb = r0 + g; rb < r1; rb += 4L * groups) {
-        long long tok[4];
-        float x[4];
+      constexpr int kU = 8;   // rows in flight per thread
+      for (long rb = r0 + g; rb < r1; rb += (long)kU * groups) {
+        long long tok[kU];
+        float x[kU];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {   // 4 rows in flight
+        for (int u = 0; u < kU; ++u) {
           const long r = rb + (long)u * groups;
           tok[u] = pad;
           x[u] = 0.f;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < kU; ++u)
           if (tok[u] != pad) mine[tok[u] * Wd] += x[u];
       }
     }

@@ -478,3 +478,29 @@ def test_fork_join_streams_keep_stream_semantics():
         assert torch.equal(logp, ref[0])
         assert (grads - ref[1]).norm() <= 1e-5 * ref[1].norm()
         assert abs(float(loss) - float(ref[2])) <= 1e-6 * abs(float(ref[2]))
+
+
+FALLBACK_ENVS = [
+    {"GSCAN_SHADOW": "0"},                                   # grouped weight-gradient GEMM after the sweep only
+    {"GSCAN_SHADOW_CUTS": "45"},                             # one progress signal instead of three
+    {"GSCAN_SHADOW_CUTS": "80,60,40,20"},                    # four
+    {"GSCAN_NO_GROUP_GEMM": "1", "GSCAN_SHADOW": "0"},       # one split-K launch per weight gradient
+    {"GSCAN_ENC_STREAMING": "1"},                            # encoder sweeps that stream W_hh from L2
+    {"GSCAN_HEAD_UNFUSED": "1"},                             # log-softmax backward + two products for the output head
+    {"GSCAN_CAP_PRELUDE": "0", "GSCAN_CAP_POST": "0", "GSCAN_MAIN_WAITS_VALUE": "0"},
+]
+
+
+@pytest.mark.parametrize("env", FALLBACK_ENVS, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_alternative_schedules_keep_parity(env):
+    """The library reads its schedule switches from the environment once per process, so every alternative path
+    (fallback kernels, other stream / SM-budget arrangements) reruns the full-size oracle comparison in a child
+    process: same tolerances, same inputs."""
+    import os, subprocess, sys
+    child_env = dict(os.environ, **env)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "tests/test_gpu_parity.py", "-k",
+                        "test_full_size_against_oracle and comp-True"], cwd=root, env=child_env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "1 passed" in r.stdout, r.stdout[-500:]
