@@ -206,7 +206,7 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
     L.dfeat = L.take(B * M * D);
     L.dconv = L.take(B * M * D);
     L.dWt_cnn = L.take(cs.wtotal());
-    L.progress = L.take(4);
+    L.progress = L.take(8);   // [0..3] backward sweep, [4..7] forward sweep
     L.ZV = L.take(B * M * 5 * H);
     L.ZT = L.take(Ti * B * 6 * H);
     L.WstV = L.take(5 * H * H);
@@ -916,6 +916,45 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   prof_mark(2, st);
   const ClusterCfg cc = v3_shape_ok(*d) ? ClusterCfg{} : pick_cluster_cfg(*d);
   bool v3_done = false;
+  // output projection + log-softmax of the steps [t0, t1) (rows t0*B .. t1*B of the time-major lists)
+  const size_t head_smem = (size_t)V * (H + 1) * sizeof(float);
+  if (head_smem > 48 * 1024) TRY(set_smem(out_logsoftmax_kernel, head_smem));
+  // keep_off_sweep_sms: a shadow launch must not land on the SMs of the sweep (its CTAs would share their issue slots
+  // with the latency-bound recurrence: measured +45 us on the sweep) - asking for 48 KB of shared memory makes the
+  // CTAs fit only where the sweep (185 KB) is not resident
+  auto head_rows = [&](int t0, int t1, cudaStream_t s_, bool keep_off_sweep_sms = false) -> int {
+    const long r0 = (long)t0 * B, r1 = (long)t1 * B;
+    if (r1 <= r0) return 0;
+    const size_t head_smem_l = keep_off_sweep_sms && head_smem < 48 * 1024 ? (size_t)48 * 1024 : head_smem;
+    TRY(linear(U1 + (size_t)r0 * 4 * H, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre + (size_t)r0 * H, H, (int)(r1 - r0), H,
+               4 * H, nullptr, nullptr, 0, s_));
+    const int blocks = min(ceil_div((int)(r1 - r0), 8), 8 * num_sms());
+    out_logsoftmax_kernel<<<blocks, 256, head_smem_l, s_>>>(ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.logp, nullptr,
+                                                            r0, r1);
+    GSCAN_CHECK_LAUNCH();
+    return 0;
+  };
+  const int sms_all = num_sms();
+  const int sweep_ctas = ceil_div(B, v3::kNB) * v3::kC;
+  unsigned int* fprog = reinterpret_cast<unsigned int*>(ws + L.progress) + 4;
+  int f_cut[4];
+  int n_fcut = 0;
+  {
+    // percent of Tt, ascending.  OFF by default: measured at B = 200 with cuts 35,65,90 the head stage after the sweep
+    // shrinks from 60 to 32 us, but the forward sweep itself slows from 0.952 to 0.999 ms with the GEMM beside it
+    // (the shadow CTAs kept off the sweep's SMs or not) - a net loss of 18 us per step.
+    const char* spec = getenv("GSCAN_SHADOW_FWD_CUTS");
+    if (!spec) spec = "";
+    int prev = 0;
+    for (const char* q = spec; *q && n_fcut < 4;) {
+      const int t = atoi(q) * Tt / 100;
+      if (t > prev && t < Tt) { f_cut[n_fcut++] = t; prev = t; }
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+  }
+  bool shadow_fwd = S && v3_shape_ok(*d) && stream_wait_value_fn() && env_int("GSCAN_SHADOW", 1) != 0 && Tt >= 16 &&
+                    sms_all - sweep_ctas >= 8 && n_fcut > 0;
   if (v3_shape_ok(*d)) {
     v3::DecFwd3P p3{};
     p3.B = B; p3.T = Tt; p3.Ti = d->Ti;
@@ -923,9 +962,32 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
     p3.KT = p.KT; p3.KV = p.KV; p3.cmd_len = cmd_len; p3.h_init = p.h_init; p3.c_init = p.c_init; p3.Xe = p.Xe;
     p3.U = p.U; p3.Cs = p.Cs; p3.gates = p.gates; p3.alpha = p.alpha; p3.beta = p.beta;
     p3.Qp = p.Qp; p3.qT = p.qT; p3.qV = p.qV; p3.beta_sum = p.beta_sum;
+    // Shadow schedule of the output head (same mechanism as in gscan_backward): the sweep signals when the steps
+    // t < cut are stored; helper stream 2 then projects those rows of U and takes their log-softmax on the idle SMs.
+    if (shadow_fwd) {
+      TRYCUDA(cudaMemsetAsync(fprog, 0, 4 * sizeof(unsigned int), st));
+      TRY(fork_side(S, 2, st));
+      p3.progress = fprog;
+      p3.n_signals = n_fcut;
+      for (int k = 0; k < n_fcut; ++k) p3.t_signal[k] = f_cut[k];
+    }
     int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, false, st);
     if (rc == 0) v3_done = true;
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
+    if (shadow_fwd && !v3_done) {
+      shadow_fwd = false;
+      TRY(join_side(S, 2, st));
+    }
+    if (shadow_fwd) {
+      cudaStream_t sh = S->s[2];
+      tc::ScopedSmCap cap(sms_all - sweep_ctas);
+      for (int k = 0; k < n_fcut; ++k) {
+        if (stream_wait_value_fn()((CUstream)sh, (CUdeviceptr)(fprog + k), (cuuint32_t)sweep_ctas, 0u /* GEQ */) != CUDA_SUCCESS)
+          return GSCAN_E_UNSUPPORTED;
+        TRY(head_rows(k == 0 ? 0 : f_cut[k - 1], f_cut[k], sh, true));
+      }
+      chain_mark("s2:shadow_head", sh);
+    }
   }
   if (v3_done) {
   } else if (cc.C) {
@@ -941,16 +1003,10 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   }
   prof_mark(3, st);
   chain_mark("m:sweep_done", st);
-  // output projection for all steps at once, then log-softmax
-  TRY(linear(U1, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre, H, Tt * B, H, 4 * H, nullptr, nullptr, 0, st));
-  {
-    size_t smem = (size_t)V * (H + 1) * sizeof(float);
-    if (smem > 48 * 1024) TRY(set_smem(out_logsoftmax_kernel, smem));
-    int blocks = min(ceil_div(Tt * B, 8), 8 * num_sms());
-    out_logsoftmax_kernel<<<blocks, 256, smem, st>>>(ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.logp, nullptr);
-    GSCAN_CHECK_LAUNCH();
-    TRYCUDA(cudaMemcpyAsync(logp, ws + L.logp, sizeof(float) * (size_t)B * Tt * V, cudaMemcpyDeviceToDevice, st));
-  }
+  // output projection + log-softmax: the steps the shadow launches did not cover, or all of them
+  TRY(head_rows(shadow_fwd ? f_cut[n_fcut - 1] : 0, Tt, st));
+  if (shadow_fwd) TRY(join_side(S, 2, st));
+  TRYCUDA(cudaMemcpyAsync(logp, ws + L.logp, sizeof(float) * (size_t)B * Tt * V, cudaMemcpyDeviceToDevice, st));
   if (d->auxiliary_task) {
     row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(ws + L.beta_sum, M, B, ws + L.aux_logp);
     GSCAN_CHECK_LAUNCH();

@@ -137,13 +137,14 @@ constexpr int kMaxVPerLane = 4;
 
 __global__ void __launch_bounds__(256) out_logsoftmax_kernel(const float* __restrict__ pre, const float* __restrict__ Wh2o,
                                                              int H, int V, int B, int T, float* __restrict__ logp,
-                                                             float* __restrict__ logits_out /* [R][V] or null */) {
+                                                             float* __restrict__ logits_out /* [R][V] or null */,
+                                                             long row_begin = 0, long row_end = -1) {
   extern __shared__ __align__(16) float w_s[];   // [V][H+1]
   for (int i = threadIdx.x; i < V * H; i += blockDim.x) w_s[(i / H) * (H + 1) + (i % H)] = __ldg(Wh2o + i);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long R = (long)B * T;
-  for (long row = (long)blockIdx.x * (blockDim.x >> 5) + warp; row < R; row += (long)gridDim.x * (blockDim.x >> 5)) {
+  const long R = row_end >= 0 ? row_end : (long)B * T;   // rows [row_begin, R) of the time-major list
+  for (long row = row_begin + (long)blockIdx.x * (blockDim.x >> 5) + warp; row < R; row += (long)gridDim.x * (blockDim.x >> 5)) {
     const float* x = pre + row * H;
     float l[kMaxVPerLane];
 #pragma unroll
