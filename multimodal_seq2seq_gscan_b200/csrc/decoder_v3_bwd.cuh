@@ -663,6 +663,8 @@ struct ValueZP {
   int B, T, Ti, H, NC;               // NC = 5H or 6H columns of X
   float *ZV, *ZT;                    // [B*36][ldv], [Ti*B][ldt]
   int ldv, ldt;
+  int t_begin, t_end;                // steps summed by this launch (0, T for all of them)
+  int accumulate;                    // add to ZV / ZT (partial sums of an earlier launch over other steps)
 };
 
 // grid = (B, ceil(NC/4 / 64)), 256 threads.  Thread = (column quad, weight group wg): lane = 8 column quads x 4
@@ -687,7 +689,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // unused slots hold zeros, so the inner loop is branch-free and the same for every lane.  Steps are padded to a
 // multiple of 4 with zero weights AND zero X (a stale ring slot could hold a NaN).
 inline int value_z_qw(int Ti) { return Ti <= 12 ? 3 : 4; }
-inline size_t value_z_smem_bytes(int T, int Ti) {
+inline size_t value_z_smem_bytes(int T, int Ti) {   // T = steps of one launch
   const int Tp = (T + 3) & ~3;
   return sizeof(float) * ((size_t)Tp * 16 * value_z_qw(Ti) + (size_t)kZRing * 4 * 64 * 4);
 }
@@ -696,7 +698,7 @@ template <int QW>
 __global__ void __launch_bounds__(256, 2) attn_value_z_kernel(ValueZP p) {
   constexpr int ZS = 16 * QW;                      // weight slots per step
   extern __shared__ __align__(16) float zw_s[];   // [Tp][ZS] weights, then the ring [kZRing][4 steps][64 quads] float4
-  const int b = blockIdx.x, B = p.B, T = p.T, Ti = p.Ti, H = p.H;
+  const int b = blockIdx.x, B = p.B, T = p.t_end - p.t_begin, Ti = p.Ti, H = p.H;   // local step tl = t - t_begin
   const int Tp = (T + 3) & ~3, nr = Tp / 4;
   float4* ring = reinterpret_cast<float4*>(zw_s + (size_t)Tp * ZS);
   const int wg = threadIdx.x & 3, ql = threadIdx.x >> 2;
@@ -708,7 +710,7 @@ __global__ void __launch_bounds__(256, 2) attn_value_z_kernel(ValueZP p) {
     if (c < 4 * H) { src = p.dgates + c; }
     else if (c < 5 * H) { src = p.dpre + (c - 4 * H); ld = H; }
     else { src = p.dd + (c - 5 * H); ld = H; }
-    src += (size_t)b * ld;
+    src += ((size_t)p.t_begin * B + b) * ld;
   }
   const size_t step = (size_t)B * ld;
   // lane wg of a quad's 4 lanes fetches step 4r + wg of round r; all 4 lanes consume all 4 steps
@@ -725,8 +727,8 @@ __global__ void __launch_bounds__(256, 2) attn_value_z_kernel(ValueZP p) {
   // load -> store loop here cost 30 us of exposed latency
   for (int i = threadIdx.x; i < Tp * ZS; i += blockDim.x) {
     const int t = i / ZS, k = i - t * ZS;
-    if (t < T && k < kM) cp_async4(zw_s + i, p.beta + ((size_t)t * B + b) * kM + k);
-    else if (t < T && k - kM < Ti) cp_async4(zw_s + i, p.alpha + ((size_t)t * B + b) * Ti + (k - kM));
+    if (t < T && k < kM) cp_async4(zw_s + i, p.beta + ((size_t)(p.t_begin + t) * B + b) * kM + k);
+    else if (t < T && k - kM < Ti) cp_async4(zw_s + i, p.alpha + ((size_t)(p.t_begin + t) * B + b) * Ti + (k - kM));
     else zw_s[i] = 0.f;
   }
   cp_async_commit();
@@ -769,11 +771,16 @@ __global__ void __launch_bounds__(256, 2) attn_value_z_kernel(ValueZP p) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int widx = 4 * (wg + 4 * q) + k;     // 0..35 beta, 36.. alpha
-      const float4 o = make_float4(acc[q][k][0].x, acc[q][k][0].y, acc[q][k][1].x, acc[q][k][1].y);
+      float4 o = make_float4(acc[q][k][0].x, acc[q][k][0].y, acc[q][k][1].x, acc[q][k][1].y);
+      float4* dst = nullptr;
       if (widx < kM) {
-        if (c < p.ldv) *reinterpret_cast<float4*>(p.ZV + ((size_t)b * kM + widx) * p.ldv + c) = o;
+        if (c < p.ldv) dst = reinterpret_cast<float4*>(p.ZV + ((size_t)b * kM + widx) * p.ldv + c);
       } else if (widx - kM < Ti) {
-        *reinterpret_cast<float4*>(p.ZT + ((size_t)(widx - kM) * B + b) * p.ldt + c) = o;
+        dst = reinterpret_cast<float4*>(p.ZT + ((size_t)(widx - kM) * B + b) * p.ldt + c);
+      }
+      if (dst) {
+        if (p.accumulate) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        *dst = o;
       }
     }
   }

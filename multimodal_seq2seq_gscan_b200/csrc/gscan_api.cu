@@ -1124,6 +1124,37 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     const int rows = ((k == 0 ? Tt : t_cut[k - 1]) - (k == n_cut ? 0 : t_cut[k])) * B;
     for (int i = 0; shadow && i < ngp; ++i) shadow = rows >= 1024 && tc::group_eligible(gp[i], rows);
   }
+  // one launch of the value-path Z kernel (decoder_v3_bwd.cuh) over the steps [t0, t1)
+  const int zNC = (d->conditional_attention ? 6 : 5) * H;
+  auto launch_z = [&](int t0, int t1, bool accumulate, cudaStream_t s_, bool keep_off_sweep_sms = false) -> int {
+    if (t1 <= t0) return 0;
+    v3::ValueZP zp{};
+    zp.dgates = ws + L.dgates; zp.dpre = ws + L.dpre; zp.dd = ws + L.dd;
+    zp.alpha = ws + L.alpha; zp.beta = ws + L.beta;
+    zp.B = B; zp.T = Tt; zp.Ti = Ti; zp.H = H; zp.NC = zNC;
+    zp.ZV = ws + L.ZV; zp.ZT = ws + L.ZT; zp.ldv = 5 * H; zp.ldt = zNC;
+    zp.t_begin = t0; zp.t_end = t1; zp.accumulate = accumulate ? 1 : 0;
+    size_t smem = v3::value_z_smem_bytes(t1 - t0, Ti);
+    // a shadow launch must not become resident next to a sweep CTA (194 KB of the SM's 227 KB): ask for at least 48 KB
+    if (keep_off_sweep_sms && smem < 48 * 1024) smem = 48 * 1024;
+    const dim3 zgrid(B, ceil_div(zNC / 4, 64));
+    if (v3::value_z_qw(Ti) == 3) {
+      if (v3::value_z_smem_bytes(Tt, Ti) > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel<3>, v3::value_z_smem_bytes(Tt, Ti)));
+      v3::attn_value_z_kernel<3><<<zgrid, 256, smem, s_>>>(zp);
+    } else {
+      if (v3::value_z_smem_bytes(Tt, Ti) > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel<4>, v3::value_z_smem_bytes(Tt, Ti)));
+      v3::attn_value_z_kernel<4><<<zgrid, 256, smem, s_>>>(zp);
+    }
+    GSCAN_CHECK_LAUNCH();
+    return 0;
+  };
+  // What goes into the shadow: the grouped GEMM of every chunk.  GSCAN_SHADOW_Z=1 also puts the Z kernel of every
+  // chunk there (it heads the chain everything after the sweep waits for) and the grouped GEMM of only the first
+  // GSCAN_SHADOW_GROUP_CHUNKS chunks - measured a LOSS (2.975 ms/step with 2 GEMM chunks, 2.884 with 1, against 2.848
+  // without): on 23 SMs the latency-bound Z launches run past the end of the sweep and the last partial sum, which
+  // the whole post-sweep chain waits for, arrives later than the single full-chip launch does.  Off by default.
+  const bool shadow_z = env_int("GSCAN_SHADOW_Z", 0) != 0;
+  const int group_chunks = shadow_z ? min(n_cut, env_int("GSCAN_SHADOW_GROUP_CHUNKS", 2)) : n_cut;
   unsigned int* progress = reinterpret_cast<unsigned int*>(ws + L.progress);
   if (shadow) {
     TRYCUDA(cudaMemsetAsync(progress, 0, 4 * sizeof(unsigned int), st));
@@ -1162,6 +1193,8 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
             CUDA_SUCCESS)
           return GSCAN_E_UNSUPPORTED;
         const int t0 = t_cut[k], t1 = k == 0 ? Tt : t_cut[k - 1];
+        if (shadow_z) TRY(launch_z(t0, t1, k > 0, sh, true));
+        if (k >= group_chunks) continue;
         tc::GroupProblem part[tc::MAXG];
         const size_t r0 = (size_t)t0 * B;
         for (int i = 0; i < ngp; ++i) {
@@ -1171,7 +1204,8 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
         }
         TRY(tc::launch_group_tn(part, ngp, (t1 - t0) * B, sh, false, idle_sms));   // units = tiles x idle SMs: even rounds
       }
-      chain_mark("s2:shadow_group", sh);
+      if (shadow_z) TRYCUDA(cudaEventRecord(S->join_ev[2], sh));   // partial Z sums of the steps >= the last cut
+      chain_mark("s2:shadow_end", sh);
     }
   }
   // Three independent chains from here, joined before returning:
@@ -1193,21 +1227,12 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
           P[GSCAN_P_DEC_WIH], P[GSCAN_P_O2H_W], d->conditional_attention ? P[GSCAN_P_COND_W] : nullptr, H, ws + L.WstV,
           ws + L.WstT);
       GSCAN_CHECK_LAUNCH();
-      v3::ValueZP zp{};
-      zp.dgates = ws + L.dgates; zp.dpre = ws + L.dpre; zp.dd = ws + L.dd;
-      zp.alpha = ws + L.alpha; zp.beta = ws + L.beta;
-      zp.B = B; zp.T = Tt; zp.Ti = Ti; zp.H = H; zp.NC = NC;
-      zp.ZV = ws + L.ZV; zp.ZT = ws + L.ZT; zp.ldv = 5 * H; zp.ldt = NC;
-      const size_t smem = v3::value_z_smem_bytes(Tt, Ti);
-      const dim3 zgrid(B, ceil_div(NC / 4, 64));
-      if (v3::value_z_qw(Ti) == 3) {
-        if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel<3>, smem));
-        v3::attn_value_z_kernel<3><<<zgrid, 256, smem, sv>>>(zp);
+      if (shadow && shadow_z) {   // the steps the shadow launches did not cover, added to their partial sums
+        TRYCUDA(cudaStreamWaitEvent(sv, S->join_ev[2], 0));
+        TRY(launch_z(0, t_cut[n_cut - 1], true, sv));
       } else {
-        if (smem > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel<4>, smem));
-        v3::attn_value_z_kernel<4><<<zgrid, 256, smem, sv>>>(zp);
+        TRY(launch_z(0, Tt, false, sv));
       }
-      GSCAN_CHECK_LAUNCH();
       chain_mark("s0:Z", sv);
       // split-K (atomic adds onto the key-path part the sweep stored): short K loops on more SMs
       TRY(launch_gemm(ws + L.ZV, 5 * H, 1, ws + L.WstV, H, 1, ws + L.dKV, H, B * M, H, 5 * H, nullptr, nullptr, 0, 0, 2, sv));
@@ -1238,7 +1263,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     // everything downstream on both helper streams hangs off the value path: it gets the chip first
     static const bool main_waits = env_int("GSCAN_MAIN_WAITS_VALUE", 1) != 0;
     if (wait_value_path && main_waits) TRYCUDA(cudaStreamWaitEvent(st, S->join_ev[0], 0));
-    if (shadow) TRY(tc::launch_group_tn(gp, ngp, t_cut[n_cut - 1] * B, st, false, 0));
+    if (shadow) TRY(tc::launch_group_tn(gp, ngp, t_cut[group_chunks - 1] * B, st, false, 0));
     else TRY(launch_grad_group(gp, ngp, R, sms, st));
   }
   chain_mark("m:group", st);

@@ -482,6 +482,7 @@ def test_fork_join_streams_keep_stream_semantics():
 
 FALLBACK_ENVS = [
     {"GSCAN_SHADOW": "0"},                                   # grouped weight-gradient GEMM after the sweep only
+    {"GSCAN_SHADOW_Z": "1"},                                 # value-path Z kernel chunked into the shadow too (off by default)
     {"GSCAN_SHADOW_CUTS": "45"},                             # one progress signal instead of three
     {"GSCAN_SHADOW_CUTS": "80,60,40,20"},                    # four
     {"GSCAN_SHADOW_FWD_CUTS": "35,65,90"},                   # output head in the shadow of the forward sweep (off by default)
