@@ -1335,6 +1335,16 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   ep.dh_enc = ws + L.dh_enc;
   TRY(launch_enc(*d, ep, true, stx));
   chain_mark("s1:enc_bwd", stx);
+  // From here the chain splits: the embedding gradient stays on helper stream 1, the encoder weight gradients (which
+  // nothing waits for) move to helper stream 2, idle since its shadow launches ended.  (One stream: joined at +423 us
+  // after the sweep, 57 us after the caller's own chain.)
+  cudaStream_t sw = stx;
+  static const bool split_tail = env_int("GSCAN_SPLIT_ENC_TAIL", 1) != 0;
+  if (S && split_tail) {
+    sw = S->s[2];
+    TRYCUDA(cudaEventRecord(S->fork_ev[2], stx));
+    TRYCUDA(cudaStreamWaitEvent(sw, S->fork_ev[2], 0));
+  }
   const int wih[2] = {GSCAN_P_ENC_WIH, GSCAN_P_ENC_WIH_R}, whh[2] = {GSCAN_P_ENC_WHH, GSCAN_P_ENC_WHH_R};
   const int bih[2] = {GSCAN_P_ENC_BIH, GSCAN_P_ENC_BIH_R}, bhh[2] = {GSCAN_P_ENC_BHH, GSCAN_P_ENC_BHH_R};
   // embedding gradient first (it is what the rest of this chain waits for): both directions add into the zeroed
@@ -1358,18 +1368,19 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       gp[n++] = {ws + L.dga[i], 4 * H, ws + L.hprev[i], H, G[whh[i]], H, 4 * H, H};
       gp[n++] = {ws + L.dga[i], 4 * H, ws + L.enc_x, E, G[wih[i]], E, 4 * H, E};
     }
-    TRY(launch_grad_group(gp, n, RE, sms, stx));
+    TRY(launch_grad_group(gp, n, RE, sms, sw));
     for (int i = 0; i < 2; ++i) {
-      TRY(launch_colsum(ws + L.dga[i], 4 * H, RE, 4 * H, G[bih[i]], stx));
-      TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, stx));
+      TRY(launch_colsum(ws + L.dga[i], 4 * H, RE, 4 * H, G[bih[i]], sw));
+      TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, sw));
     }
   }
-  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, stx));
-  chain_mark("s1:enc_wgrad", stx);
+  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, sw));
+  chain_mark("enc_wgrad", sw);
+  chain_mark("s1:end", stx);
   if (S) {
     TRY(join_side(S, 0, st));
     TRY(join_side(S, 1, st));
-    if (shadow) TRY(join_side(S, 2, st));
+    if (shadow || sw != stx) TRY(join_side(S, 2, st));
   }
   prof_mark(9, st);
   chain_mark("joined", st);
