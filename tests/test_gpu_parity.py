@@ -480,6 +480,32 @@ def test_fork_join_streams_keep_stream_semantics():
         assert abs(float(loss) - float(ref[2])) <= 1e-6 * abs(float(ref[2]))
 
 
+
+@pytest.mark.parametrize("B,tmax,lo", [(100, 60, 20), (136, 40, 10), (33, 121, 60), (200, 30, 5)])
+def test_medium_shapes_against_oracle(B, tmax, lo):
+    """Shapes between the tiny golden cases and the full-size one: the number of clusters of the sweeps (and with it
+    the SMs left idle for the shadow launches), the rows per shadow chunk and the K-splits of the grouped
+    weight-gradient GEMM all depend on B and Tt; the cut-off below which the shadow schedule is not used at all
+    (1,024 rows per chunk) falls inside this set."""
+    cfg = dict(O.CONFIGS["comp"])
+    cfg["auxiliary_task"] = True
+    params = O.synthetic_params(cfg, 77, scale=1.5)
+    batch = O.synthetic_batch(cfg, batch_size=B, seed=78, max_tgt_len=tmax, min_tgt_len=lo)
+    model = build_model(cfg, params, train=True)
+    d = to_dev(batch)
+    logp, aux = model(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                      situations_input=d["situations"], target_batch=d["targets"], target_lengths=batch["tgt_lengths"])
+    loss = model.get_loss(logp, d["targets"]) + 0.3 * model.get_auxiliary_loss(aux, d["positions"])
+    loss.backward()
+    logp_o, aux_o, loss_o, grads_o = oracle_run(cfg, params, batch)
+    assert (logp.detach().cpu().double() - logp_o).abs().max() <= LOGP_ATOL
+    assert (aux.detach().cpu().double() - aux_o).abs().max() <= LOGP_ATOL
+    named = dict(model.named_parameters())
+    for pname, _ in O.param_shapes(cfg):
+        err = rel_l2(named[pname].grad, grads_o[pname])
+        assert err <= GRAD_RTOL, f"B={B} Tt={tmax} {pname}: rel-L2 {err:.3e}"
+
+
 FALLBACK_ENVS = [
     {"GSCAN_SHADOW": "0"},                                   # grouped weight-gradient GEMM after the sweep only
     {"GSCAN_SHADOW_Z": "1"},                                 # value-path Z kernel chunked into the shadow too (off by default)
