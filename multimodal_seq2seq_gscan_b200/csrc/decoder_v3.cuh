@@ -175,11 +175,6 @@ struct DecFwd3P {
   const float* Xe;                // [T][B][4H]
   float *U, *Cs, *gates, *alpha, *beta, *Qp, *qT, *qV, *beta_sum;   // saved activations (recurrent.cuh DecFwdP)
   long long* timeline;   // debug: [T][16] clock64 stamps of CTA 0, else null
-  // progress signals (teacher forcing only): every CTA adds 1 to progress[k] once its stores of the steps
-  // t < t_signal[k] (ascending) are fenced; the host starts the output projection of those rows beside the sweep
-  unsigned int* progress;
-  int n_signals;
-  int t_signal[4];
   // greedy decoding (predict.py:97-117); tables as in recurrent.cuh DecFwdP
   const float *XeTab, *OutE, *Wo_t;
   int V, Vp, sos, eos;
@@ -764,17 +759,6 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     GSCAN3_STAMP(14);
-    if (!GREEDY && p.progress != nullptr) {
-      int sig = -1;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (k < p.n_signals && t + 1 == p.t_signal[k]) sig = k;
-      if (sig >= 0) {   // block-uniform; 3 extra barriers per sweep
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) atomicAdd(p.progress + sig, 1u);
-      }
-    }
     if (GREEDY) {
       // ---- logits = OutE[tok] + Wout[:, H:4H] . [h; c_T; c_V]: partial sums over this CTA's slices (X7), argmax, feed back ----
       __syncthreads();

@@ -206,7 +206,7 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
     L.dfeat = L.take(B * M * D);
     L.dconv = L.take(B * M * D);
     L.dWt_cnn = L.take(cs.wtotal());
-    L.progress = L.take(8);   // [0..3] backward sweep, [4..7] forward sweep
+    L.progress = L.take(4);
     L.ZV = L.take(B * M * 5 * H);
     L.ZT = L.take(Ti * B * 6 * H);
     L.WstV = L.take(5 * H * H);
@@ -889,8 +889,13 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
   {
     long n = (long)B * Tt * H;
-    embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sp>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
-                                                              4 * H, B, Tt, 1);
+    const bool vec4 = (H & 3) == 0 && aligned16(P[GSCAN_P_DEC_EMB]) && (!drop_dec || aligned16(drop_dec));
+    if (vec4)
+      embed4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, sp>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
+                                                                     4 * H, B, Tt, 1);
+    else
+      embed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sp>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
+                                                                4 * H, B, Tt, 1);
     GSCAN_CHECK_LAUNCH();
   }
   float* U1 = ws + L.U + (size_t)B * 4 * H;
@@ -934,27 +939,6 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
     GSCAN_CHECK_LAUNCH();
     return 0;
   };
-  const int sms_all = num_sms();
-  const int sweep_ctas = ceil_div(B, v3::kNB) * v3::kC;
-  unsigned int* fprog = reinterpret_cast<unsigned int*>(ws + L.progress) + 4;
-  int f_cut[4];
-  int n_fcut = 0;
-  {
-    // percent of Tt, ascending.  OFF by default: measured at B = 200 with cuts 35,65,90 the head stage after the sweep
-    // shrinks from 60 to 32 us, but the forward sweep itself slows from 0.952 to 0.999 ms with the GEMM beside it
-    // (the shadow CTAs kept off the sweep's SMs or not) - a net loss of 18 us per step.
-    const char* spec = getenv("GSCAN_SHADOW_FWD_CUTS");
-    if (!spec) spec = "";
-    int prev = 0;
-    for (const char* q = spec; *q && n_fcut < 4;) {
-      const int t = atoi(q) * Tt / 100;
-      if (t > prev && t < Tt) { f_cut[n_fcut++] = t; prev = t; }
-      while (*q && *q != ',') ++q;
-      if (*q == ',') ++q;
-    }
-  }
-  bool shadow_fwd = S && v3_shape_ok(*d) && stream_wait_value_fn() && env_int("GSCAN_SHADOW", 1) != 0 && Tt >= 16 &&
-                    sms_all - sweep_ctas >= 8 && n_fcut > 0;
   if (v3_shape_ok(*d)) {
     v3::DecFwd3P p3{};
     p3.B = B; p3.T = Tt; p3.Ti = d->Ti;
@@ -962,32 +946,9 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
     p3.KT = p.KT; p3.KV = p.KV; p3.cmd_len = cmd_len; p3.h_init = p.h_init; p3.c_init = p.c_init; p3.Xe = p.Xe;
     p3.U = p.U; p3.Cs = p.Cs; p3.gates = p.gates; p3.alpha = p.alpha; p3.beta = p.beta;
     p3.Qp = p.Qp; p3.qT = p.qT; p3.qV = p.qV; p3.beta_sum = p.beta_sum;
-    // Shadow schedule of the output head (same mechanism as in gscan_backward): the sweep signals when the steps
-    // t < cut are stored; helper stream 2 then projects those rows of U and takes their log-softmax on the idle SMs.
-    if (shadow_fwd) {
-      TRYCUDA(cudaMemsetAsync(fprog, 0, 4 * sizeof(unsigned int), st));
-      TRY(fork_side(S, 2, st));
-      p3.progress = fprog;
-      p3.n_signals = n_fcut;
-      for (int k = 0; k < n_fcut; ++k) p3.t_signal[k] = f_cut[k];
-    }
     int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, false, st);
     if (rc == 0) v3_done = true;
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
-    if (shadow_fwd && !v3_done) {
-      shadow_fwd = false;
-      TRY(join_side(S, 2, st));
-    }
-    if (shadow_fwd) {
-      cudaStream_t sh = S->s[2];
-      tc::ScopedSmCap cap(sms_all - sweep_ctas);
-      for (int k = 0; k < n_fcut; ++k) {
-        if (stream_wait_value_fn()((CUstream)sh, (CUdeviceptr)(fprog + k), (cuuint32_t)sweep_ctas, 0u /* GEQ */) != CUDA_SUCCESS)
-          return GSCAN_E_UNSUPPORTED;
-        TRY(head_rows(k == 0 ? 0 : f_cut[k - 1], f_cut[k], sh, true));
-      }
-      chain_mark("s2:shadow_head", sh);
-    }
   }
   if (v3_done) {
   } else if (cc.C) {
@@ -1003,9 +964,9 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   }
   prof_mark(3, st);
   chain_mark("m:sweep_done", st);
-  // output projection + log-softmax: the steps the shadow launches did not cover, or all of them
-  TRY(head_rows(shadow_fwd ? f_cut[n_fcut - 1] : 0, Tt, st));
-  if (shadow_fwd) TRY(join_side(S, 2, st));
+  // output projection for all steps at once, then log-softmax.  (Chunks of it in the shadow of the forward sweep, the
+  // way the backward pass does it, were a net loss: DESIGN.md 4.5 - and the signal code alone cost the sweep 33 us.)
+  TRY(head_rows(0, Tt, st));
   TRYCUDA(cudaMemcpyAsync(logp, ws + L.logp, sizeof(float) * (size_t)B * Tt * V, cudaMemcpyDeviceToDevice, st));
   if (d->auxiliary_task) {
     row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(ws + L.beta_sum, M, B, ws + L.aux_logp);

@@ -58,6 +58,26 @@ __global__ void embed_kernel(const long long* __restrict__ tokens, int tok_strid
   out[orow * ldo + h] = v;
 }
 
+// 4 elements per thread (Wd % 4 == 0, 16-byte aligned rows): a quarter of the threads and 128-bit accesses
+__global__ void embed4_kernel(const long long* __restrict__ tokens, int tok_stride, const float* __restrict__ W,
+                              int Wd, const float* __restrict__ mask, float* __restrict__ out, long ldo,
+                              int B, int T, int row_mode) {
+  const int Wq = Wd >> 2;
+  long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long)B * T * Wq) return;
+  int hq = idx % Wq;
+  long r = idx / Wq;
+  int b = r / T, t = r - (long)b * T;
+  long long tok = tokens[(long)b * tok_stride + t];
+  float4 v = __ldg(reinterpret_cast<const float4*>(W + tok * Wd) + hq);
+  if (mask) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mask + r * Wd) + hq);
+    v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+  }
+  long orow = row_mode == 0 ? r : ((long)(t + 1) * B + b);
+  reinterpret_cast<float4*>(out + orow * ldo)[hq] = v;
+}
+
 // Embedding scatter-add: dW[tok][h] += mask * dX[row][h] for tok != pad.  dW zeroed by host.
 // Each CTA walks a chunk of rows.  use_smem: thread (g, h) = (tid / Wd, tid % Wd) owns column h of a private copy g of
 // the table in shared memory ([groups][Vsz][Wd] floats) and walks the rows r0 + g, r0 + g + groups, ... with plain
@@ -317,10 +337,11 @@ __global__ void __launch_bounds__(1024) nll_forward_kernel(const float* __restri
   __shared__ float s_cnt[32];
   float sum = 0.f, cnt = 0.f;
   const long R = (long)B * T;
-  for (long rb = threadIdx.x; rb < R; rb += 4L * blockDim.x) {
-    long long y[4];
+  constexpr int kU = 8;   // rows in flight per thread: all targets first, then all log-probs (two dependent latencies per pass)
+  for (long rb = threadIdx.x; rb < R; rb += (long)kU * blockDim.x) {
+    long long y[kU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {   // all targets first, then all log-probs: 4 dependent pairs in flight
+    for (int u = 0; u < kU; ++u) {
       const long r = rb + (long)u * blockDim.x;
       y[u] = pad;
       if (r < R) {
@@ -328,11 +349,15 @@ __global__ void __launch_bounds__(1024) nll_forward_kernel(const float* __restri
         if (t + shift < T) y[u] = tgt[(long)b * T + t + shift];
       }
     }
+    float lp[kU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kU; ++u) {
       const long r = rb + (long)u * blockDim.x;
-      if (y[u] != pad) { sum -= __ldg(logp + r * V + y[u]); cnt += 1.f; }
+      lp[u] = y[u] != pad ? __ldg(logp + r * V + y[u]) : 0.f;
     }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (y[u] != pad) { sum -= lp[u]; cnt += 1.f; }
   }
   sum = warp_sum(sum); cnt = warp_sum(cnt);
   if ((threadIdx.x & 31) == 0) { s_sum[threadIdx.x >> 5] = sum; s_cnt[threadIdx.x >> 5] = cnt; }

@@ -65,9 +65,23 @@ def make_dims(cfg: dict, B: int, Ti: int, Tt: int, Ti_stride: int) -> Dims:
     return d
 
 
+_ONES: dict = {}
+
+
 def _dropout_mask(shape, p: float, device, generator=None) -> Optional[torch.Tensor]:
+    """Inverted-dropout mask (0 or 1/(1-p)).  Without an explicit generator it is ONE fused kernel - dropout of a cached
+    tensor of ones - instead of bernoulli_ + mul_ (the three masks of a step are drawn at its very start, on the
+    critical path: 6 launches, 28 us on B200, became 3)."""
     if p <= 0.0:
         return None
+    if generator is None:
+        key = (tuple(shape), str(device))
+        ones = _ONES.get(key)
+        if ones is None:
+            if len(_ONES) > 64:
+                _ONES.clear()
+            ones = _ONES[key] = torch.ones(shape, dtype=torch.float32, device=device)
+        return torch.nn.functional.dropout(ones, p, True)
     mask = torch.empty(shape, dtype=torch.float32, device=device)
     mask.bernoulli_(1.0 - p, generator=generator)
     return mask.mul_(1.0 / (1.0 - p))

@@ -511,7 +511,6 @@ FALLBACK_ENVS = [
     {"GSCAN_SHADOW_Z": "1"},                                 # value-path Z kernel chunked into the shadow too (off by default)
     {"GSCAN_SHADOW_CUTS": "45"},                             # one progress signal instead of three
     {"GSCAN_SHADOW_CUTS": "80,60,40,20"},                    # four
-    {"GSCAN_SHADOW_FWD_CUTS": "35,65,90"},                   # output head in the shadow of the forward sweep (off by default)
     {"GSCAN_NO_GROUP_GEMM": "1", "GSCAN_SHADOW": "0"},       # one split-K launch per weight gradient
     {"GSCAN_ENC_STREAMING": "1"},                            # encoder sweeps that stream W_hh from L2
     {"GSCAN_HEAD_UNFUSED": "1"},                             # log-softmax backward + two products for the output head
