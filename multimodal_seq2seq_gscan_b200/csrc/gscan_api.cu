@@ -1151,8 +1151,12 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       tc::ScopedSmCap cap(idle_sms);
       for (int k = 0; k < n_cut; ++k) {
         if (stream_wait_value_fn()((CUstream)sh, (CUdeviceptr)(progress + k), (cuuint32_t)sweep_ctas, 0u /* GEQ */) !=
-            CUDA_SUCCESS)
-          return GSCAN_E_UNSUPPORTED;
+            CUDA_SUCCESS) {
+          if (k > 0) return GSCAN_E_UNSUPPORTED;   // (a driver that accepted the first wait accepts the next)
+          shadow = false;                          // stream memory operations unavailable: everything after the sweep
+          TRY(join_side(S, 2, st));
+          break;
+        }
         const int t0 = t_cut[k], t1 = k == 0 ? Tt : t_cut[k - 1];
         if (shadow_z) TRY(launch_z(t0, t1, k > 0, sh, true));
         if (k >= group_chunks) continue;
@@ -1165,7 +1169,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
         }
         TRY(tc::launch_group_tn(part, ngp, (t1 - t0) * B, sh, false, idle_sms));   // units = tiles x idle SMs: even rounds
       }
-      if (shadow_z) TRYCUDA(cudaEventRecord(S->join_ev[2], sh));   // partial Z sums of the steps >= the last cut
+      if (shadow && shadow_z) TRYCUDA(cudaEventRecord(S->join_ev[2], sh));   // partial Z sums of the steps >= the last cut
       chain_mark("s2:shadow_end", sh);
     }
   }
@@ -1218,19 +1222,16 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   }
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_TXT_ENERGY_W], ws + L.dvec, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
   TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_VIS_ENERGY_W], ws + L.dvec + H, sizeof(float) * H, cudaMemcpyDeviceToDevice, st));
+  static const bool main_waits_value = env_int("GSCAN_MAIN_WAITS_VALUE", 1) != 0;
   // B5: decoder weight gradients: what the shadow launch left (rows t < t_sig), or everything
   {
     tc::ScopedSmCap cap(S ? cap_post() : 0);   // the helper chains (CNN, encoder) need SMs meanwhile
     // everything downstream on both helper streams hangs off the value path: it gets the chip first
-    static const bool main_waits = env_int("GSCAN_MAIN_WAITS_VALUE", 1) != 0;
-    if (wait_value_path && main_waits) TRYCUDA(cudaStreamWaitEvent(st, S->join_ev[0], 0));
+    if (wait_value_path && main_waits_value) TRYCUDA(cudaStreamWaitEvent(st, S->join_ev[0], 0));
     if (shadow) TRY(tc::launch_group_tn(gp, ngp, t_cut[group_chunks - 1] * B, st, false, 0));
     else TRY(launch_grad_group(gp, ngp, R, sms, st));
   }
   chain_mark("m:group", st);
-  TRY(launch_colsum(ws + L.dgates, 4 * H, R, 4 * H, G[GSCAN_P_DEC_BIH], st));
-  TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_DEC_BHH], G[GSCAN_P_DEC_BIH], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st));
-  if (d->conditional_attention) TRY(launch_colsum(ws + L.dd, H, R, H, G[GSCAN_P_COND_B], st));
   // decoder embedding: dE = dU[:, :H] + dgates . W_ih[:, :H], then scatter by token
   {
     tc::ScopedSmCap cap(S ? cap_post() : 0);
@@ -1245,6 +1246,9 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
         tgts, Tt, ws + L.dU, 4 * H, drop_dec, G[GSCAN_P_DEC_EMB], H, V, d->pad_idx_out, B, Tt, 1, rpb, use_smem);
     GSCAN_CHECK_LAUNCH();
   }
+  // text-key weight gradient: dK^T is complete once the value path is, which this stream waited for when it can
+  if (wait_value_path && !main_waits_value) TRYCUDA(cudaStreamWaitEvent(st, S->join_ev[0], 0));
+  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, st));
   chain_mark("m:dE_embed", st);
   prof_mark(8, st);
   // B6: visual keys -> CNN (helper stream 0)
@@ -1268,6 +1272,10 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
     TRY(launch_colsum(ws + L.dconv + d->F, D, B * M, d->F, G[GSCAN_P_CONV2_B], sv));
     TRY(launch_colsum(ws + L.dconv + 2 * d->F, D, B * M, d->F, G[GSCAN_P_CONV3_B], sv));
   }
+  // this chain also takes the bias column sums of the decoder (the caller's chain was the last to finish)
+  TRY(launch_colsum(ws + L.dgates, 4 * H, R, 4 * H, G[GSCAN_P_DEC_BIH], sv));
+  TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_DEC_BHH], G[GSCAN_P_DEC_BIH], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, sv));
+  if (d->conditional_attention) TRY(launch_colsum(ws + L.dd, H, R, H, G[GSCAN_P_COND_B], sv));
   chain_mark("s0:kv_cnn", sv);
   // B7: initial state and textual keys (helper stream 1).  What needs only dh0 goes first; the products on dK^T wait
   // for the value path of helper stream 0.
@@ -1335,7 +1343,6 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       TRYCUDA(cudaMemcpyAsync(G[bhh[i]], G[bih[i]], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, sw));
     }
   }
-  TRY(launch_grad_gemm(ws + L.dKT, H, ws + L.enc_out, H, G[GSCAN_P_TXT_KEY_W], H, H, H, Ti * B, sms, sw));
   chain_mark("enc_wgrad", sw);
   chain_mark("s1:end", stx);
   if (S) {
