@@ -219,6 +219,18 @@ int gscan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
                     void* stream);
 
 /*
+ * The same step with the gradient divided by a number that lives on the DEVICE: g = grad * grad_scale / *grad_denom.
+ * Data parallelism (new; the reference is single-device): every rank backpropagates the SUM form of its
+ * shard's loss into the flat buffer and appends its [n_tok, n_examples]; one all-reduce sums gradients and
+ * counts together, and grad_denom points at the summed token count inside that buffer - the normalisation of
+ * NLLLoss(ignore_index) (reference model.py:100,159) applied after the collective without a host round trip.
+ * grad_denom == NULL behaves like gscan_adam_step.
+ */
+int gscan_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                        float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                        const float* grad_denom, void* stream);
+
+/*
  * Building blocks exported for the parity tests (each is also used inside the calls above).
  */
 /* C[M,N] (ldc) = act(opA(A) . opB(B) + bias) with element (i,k) of opA at A[i*a_rs + k*a_cs] and

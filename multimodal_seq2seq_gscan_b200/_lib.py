@@ -63,6 +63,8 @@ SIGNATURES = {
     "gscan_metrics": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "gscan_adam_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
                                   c_float, c_int32, c_float, c_void_p]),
+    "gscan_adam_step_dev": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float,
+                                      c_float, c_int32, c_float, c_void_p, c_void_p]),
     "gscan_sgemm": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,
                               c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     "gscan_sgemm_path": (c_int32, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int32,

@@ -183,9 +183,13 @@ struct DecFwd3P {
   float *g_alphas, *g_betas;   // [B][T][Ti], [B][T][M] or null
 };
 
-#define GSCAN3_STAMP(k)                                                                            \
-  do {                                                                                             \
-    if (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[t * 16 + (k)] = clock64();   \
+// clock64 stamps of CTA 0 / thread 0 between the phases of a step: compiled in only for the TL = true
+// instantiations (GSCAN_TIMELINE=1), the production kernels carry no trace of them
+#define GSCAN3_STAMP(k)                                                                              \
+  do {                                                                                               \
+    if constexpr (TL) {                                                                              \
+      if (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[t * 16 + (k)] = clock64();   \
+    }                                                                                                \
   } while (0)
 
 // 4-lane mat-vec tile: rows (2 per thread) x 7 k-quads (quad 4i+ks) x 8 examples.
@@ -298,7 +302,7 @@ __device__ __forceinline__ void partial_scores(const float* __restrict__ q_s, co
   }
 }
 
-template <bool COND, bool GREEDY>
+template <bool COND, bool GREEDY, bool TL = false>
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fwd_v3_kernel(DecFwd3P p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RBl = kHS * (4 + (COND ? 1 : 0));

@@ -104,7 +104,7 @@ __device__ __forceinline__ void mv_units(const float4* __restrict__ w_lane, cons
   for (int j = 0; j < 4; ++j) o[j] = d0[j] + (d1[j] + d2[j]);
 }
 
-template <bool COND>
+template <bool COND, bool TL = false>
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bwd_v3_kernel(DecBwd3P p) {
   extern __shared__ __align__(16) float smem[];
   constexpr int RBl = kHS * (4 + (COND ? 1 : 0));

@@ -636,12 +636,12 @@ int launch_dec_fwd_cluster(const gscan_dims& d, const float* const* P, float* ws
 
 
 // ---- register-resident cluster sweep (v3, decoder_v3.cuh): H = 100, 6x6 grid only ---------------------
-template <bool COND, bool GREEDY>
+template <bool COND, bool GREEDY, bool TL = false>
 int v3_fwd_prepare(size_t bytes) {
   static bool done = false, ok = false;
   static size_t done_bytes = 0;
   if (done && bytes <= done_bytes) return ok ? 0 : GSCAN_E_UNSUPPORTED;
-  auto kern = v3::dec_fwd_v3_kernel<COND, GREEDY>;
+  auto kern = v3::dec_fwd_v3_kernel<COND, GREEDY, TL>;
   ok = false;
   done = true;
   done_bytes = bytes;
@@ -715,12 +715,15 @@ int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, con
   p.W_qV = P[GSCAN_P_VIS_QUERY_W]; p.W_ih = P[GSCAN_P_DEC_WIH];
   static const bool want_timeline = getenv("GSCAN_TIMELINE") != nullptr;   // debug only: allocates and synchronises
   long long* tl = nullptr;
-  if (want_timeline && !greedy) {
+  if (want_timeline && !greedy && cond) {   // the instrumented instantiation exists for the paper configuration only
+    TRY((v3_fwd_prepare<true, false, true>(bytes)));
     cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
     p.timeline = tl;
   }
   const int grid = ceil_div(d.B, v3::kNB) * v3::kC;
-  if (greedy) {
+  if (tl) {
+    v3::dec_fwd_v3_kernel<true, false, true><<<grid, v3::kThreads, bytes, st>>>(p);
+  } else if (greedy) {
     if (cond) v3::dec_fwd_v3_kernel<true, true><<<grid, v3::kThreads, bytes, st>>>(p);
     else v3::dec_fwd_v3_kernel<false, true><<<grid, v3::kThreads, bytes, st>>>(p);
   } else {
@@ -732,12 +735,12 @@ int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, con
   return 0;
 }
 
-template <bool COND>
+template <bool COND, bool TL = false>
 int v3_bwd_prepare(size_t bytes) {
   static bool done = false, ok = false;
   static size_t done_bytes = 0;
   if (done && bytes <= done_bytes) return ok ? 0 : GSCAN_E_UNSUPPORTED;
-  auto kern = v3::dec_bwd_v3_kernel<COND>;
+  auto kern = v3::dec_bwd_v3_kernel<COND, TL>;
   ok = false;
   done = true;
   done_bytes = bytes;
@@ -779,12 +782,14 @@ int launch_dec_bwd_v3(const gscan_dims& d, v3::DecBwd3P p, cudaStream_t st) {
   TRY(cond ? v3_bwd_prepare<true>(bytes) : v3_bwd_prepare<false>(bytes));
   static const bool want_timeline = getenv("GSCAN_TIMELINE") != nullptr;
   long long* tl = nullptr;
-  if (want_timeline) {
+  if (want_timeline && cond) {
+    TRY((v3_bwd_prepare<true, true>(bytes)));
     cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
     p.timeline = tl;
   }
   const int grid = ceil_div(d.B, v3::kNB) * v3::kC;
-  if (cond) v3::dec_bwd_v3_kernel<true><<<grid, v3::kThreads, bytes, st>>>(p);
+  if (tl) v3::dec_bwd_v3_kernel<true, true><<<grid, v3::kThreads, bytes, st>>>(p);
+  else if (cond) v3::dec_bwd_v3_kernel<true><<<grid, v3::kThreads, bytes, st>>>(p);
   else v3::dec_bwd_v3_kernel<false><<<grid, v3::kThreads, bytes, st>>>(p);
   GSCAN_CHECK_LAUNCH();
   if (tl) print_timeline("v3 bwd", tl, p.T, st);
@@ -1524,16 +1529,24 @@ int gscan_metrics(const float* logp, const int64_t* targets, int32_t B, int32_t 
   return GSCAN_OK;
 }
 
-int gscan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
-                    float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+int gscan_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                        float beta1, float beta2, float eps, int32_t step, float grad_scale, const float* grad_denom,
+                        void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return GSCAN_E_BADARG;
   if (n == 0) return GSCAN_OK;
   float bc1 = 1.f - powf(beta1, (float)step);
   float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr,
-                                                                            beta1, beta2, eps, bc1, bc2s, grad_scale);
+                                                                            beta1, beta2, eps, bc1, bc2s, grad_scale,
+                                                                            grad_denom);
   GSCAN_CHECK_LAUNCH();
   return GSCAN_OK;
+}
+
+int gscan_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                    float beta1, float beta2, float eps, int32_t step, float grad_scale, void* stream) {
+  return gscan_adam_step_dev(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, nullptr,
+                             stream);
 }
 
 int gscan_sgemm(const float* A, int64_t a_rs, int64_t a_cs, const float* B, int64_t b_rs, int64_t b_cs, float* C,

@@ -421,9 +421,10 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr, float b1, float b2, float eps,
-                            float bc1, float bc2_sqrt, float gscale) {
+                            float bc1, float bc2_sqrt, float gscale, const float* __restrict__ gdenom) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (gdenom) gscale = gscale / __ldg(gdenom);   // summed token count of the data-parallel all-reduce
   float gi = g[i] * gscale;
   float mi = b1 * m[i] + (1.f - b1) * gi;
   float vi = b2 * v[i] + (1.f - b2) * gi * gi;

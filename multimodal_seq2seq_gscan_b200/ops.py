@@ -149,7 +149,12 @@ class ModelForward(torch.autograd.Function):
         # one flat fp32 gradient buffer in model.parameters() order; the per-parameter gradients
         # returned to autograd are views into it (this is also the data-parallel all-reduce buffer)
         sizes, offsets = flat_layout(ctx.param_shapes)
-        flat = torch.zeros(int(offsets[-1]), dtype=torch.float32, device=dev)
+        n_flat = int(offsets[-1])
+        flat = _take_flat_grad_target(n_flat, dev)
+        if flat is None:
+            flat = torch.zeros(n_flat + FLAT_TAIL, dtype=torch.float32, device=dev)
+        else:
+            flat[:n_flat].zero_()      # the tail (data-parallel counts) belongs to the caller
         views = [None if s is None else flat[int(o):int(o) + n].view(s)
                  for s, o, n in zip(ctx.param_shapes, offsets[:-1], sizes)]
         rc = lib.gscan_backward(dims, _param_array(params), _ptr(commands), _ptr(cmd_len_dev), _ptr(situations),
@@ -158,6 +163,30 @@ class ModelForward(torch.autograd.Function):
         _lib.check(rc, "gscan_backward")
         _call_counts["backward"] += 1
         return (None, None, None, None, None, None, None, *views)
+
+
+# floats behind the last gradient of the flat buffer: the data-parallel step appends [n_tok, n_examples] there so
+# that gradients and counts travel in ONE all-reduce (dp.COUNT_SLOTS)
+FLAT_TAIL = 4
+_flat_grad_target: Optional[torch.Tensor] = None
+
+
+def set_flat_grad_target(buf: Optional[torch.Tensor]) -> None:
+    """The NEXT ``ModelForward.backward`` writes its flat gradient into ``buf`` (fp32, at least
+    ``flat_layout(...)[1][-1] + FLAT_TAIL`` elements; only the gradient part is zeroed) instead of a fresh
+    tensor.  ``FusedTrainer`` hands in its persistent buffer: no allocation per step, and the counts it has
+    already written into the tail survive."""
+    global _flat_grad_target
+    _flat_grad_target = buf
+
+
+def _take_flat_grad_target(n_flat: int, device) -> Optional[torch.Tensor]:
+    global _flat_grad_target
+    buf, _flat_grad_target = _flat_grad_target, None
+    if buf is None or buf.device != device or buf.dtype != torch.float32 or buf.numel() < n_flat + FLAT_TAIL \
+            or not buf.is_contiguous():
+        return None
+    return buf
 
 
 def flat_layout(shapes):
@@ -341,11 +370,13 @@ def cnn_forward(cfg, params, situations, drop_cnn=None):
     return feat
 
 
-def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0):
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step, grad_scale=1.0, grad_denom=None):
+    """One fused Adam launch over the flat buffers; ``grad_denom`` (a 1-element CUDA tensor, e.g. the all-reduced
+    token count inside the flat gradient buffer) divides the gradient on the device (gscan_adam_step_dev)."""
     lib = _lib.load()
-    _require_cuda(param, grad, exp_avg, exp_avg_sq)
+    _require_cuda(param, grad, exp_avg, exp_avg_sq, grad_denom)
     n = param.numel()
-    _lib.check(lib.gscan_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, float(lr),
-                                   float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
-                                   _stream(param.device)), "gscan_adam_step")
+    _lib.check(lib.gscan_adam_step_dev(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), n, float(lr),
+                                       float(beta1), float(beta2), float(eps), int(step), float(grad_scale),
+                                       _ptr(grad_denom), _stream(param.device)), "gscan_adam_step_dev")
     _call_counts["other"] += 1

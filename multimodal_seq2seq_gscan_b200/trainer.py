@@ -36,9 +36,13 @@ class FusedTrainer:
         self._sizes, self._offsets = sizes, offsets
         dev = self.params[0].device
         n = int(offsets[-1])
+        self._n = n
         self.flat_param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        # persistent flat gradient buffer: [gradients in parameters() order | n_tok, n_examples, 0, 0]; the backward
+        # pass writes into it (ops.set_flat_grad_target), the data-parallel all-reduce sums all of it at once
+        self.flat_grad = torch.zeros(n + dp.COUNT_SLOTS, dtype=torch.float32, device=dev)
         # re-seat every parameter as a view into the flat buffer (identity of the nn.Parameter kept)
         with torch.no_grad():
             for p, view in zip(self._present, self._views(self.flat_param)):
@@ -57,8 +61,10 @@ class FusedTrainer:
         return self.lr * self.lr_decay ** (self.step_count / self.lr_decay_steps)
 
     def _flat_gradient(self, grads):
+        """The flat buffer the per-parameter gradients are views of (what ``ModelForward.backward`` produced), or a
+        packed copy when they came from somewhere else."""
         base = grads[0]._base
-        ok = base is not None and base.numel() == self.flat_param.numel()
+        ok = base is not None and base.numel() == self._n + dp.COUNT_SLOTS
         if ok:
             for g, o in zip(grads, [o for s, o in zip(self._shapes, self._offsets[:-1]) if s is not None]):
                 if g._base is not base or g.storage_offset() != int(o):
@@ -66,39 +72,61 @@ class FusedTrainer:
                     break
         if ok:
             return base
-        flat = torch.zeros_like(self.flat_param)
+        flat = torch.zeros(self._n + dp.COUNT_SLOTS, dtype=torch.float32, device=self.flat_param.device)
         for g, view in zip(grads, self._views(flat)):
             view.copy_(g)
         return flat
 
-    def train_step(self, commands, commands_lengths, situations, targets, target_lengths, target_positions=None):
-        """One iteration: forward, loss, backward, (gradient all-reduce), Adam, LR schedule.
-        Returns the (global-batch) loss share of this rank as a 0-dim device tensor - no host sync."""
+    def train_step(self, commands, commands_lengths, situations, targets, target_lengths, target_positions=None,
+                   global_counts=None):
+        """One iteration: forward, loss, backward, (ONE all-reduce of gradients + counts), Adam, LR schedule.
+        Returns this rank's share of the global-batch loss as a 0-dim device tensor (the shares of all ranks add
+        up to the reference's loss of the global batch) - no host sync.
+
+        ``global_counts`` = (non-pad target tokens, examples) of the GLOBAL batch as numbers, when the caller knows
+        them (train.py and bench.py do): needed before the backward pass only by the auxiliary loss - without
+        them and with the auxiliary task on, a small count all-reduce runs beside the forward pass (dp.py)."""
         model = self.model
         model.train()
-        counts = work = None
-        if self.distributed:   # depends on the targets only: in flight during the forward pass
-            counts, work = dp.start_count_allreduce(targets, model.target_pad_idx, self.group)
+        n = self._n
+        use_aux = bool(model.auxiliary_task and target_positions is not None and self.weight_target_loss != 0)
+        counts_work = None
+        if self.distributed:
+            # this rank's [n_tok, n_examples] go behind the gradients NOW: they depend on the targets only
+            local = dp.local_counts(targets, model.target_pad_idx)
+            self.flat_grad[n:n + 2].copy_(local)
+            if use_aux and global_counts is None:
+                global_counts, counts_work = dp.start_count_allreduce(targets, model.target_pad_idx, self.group)
         logp, aux = model(commands_input=commands, commands_lengths=commands_lengths, situations_input=situations,
                           target_batch=targets, target_lengths=target_lengths)
         nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1)
-        aux_mean = None
-        if model.auxiliary_task and target_positions is not None and self.weight_target_loss != 0:
-            aux_mean = model.get_auxiliary_loss(aux, target_positions)
-        if work is not None:
-            work.wait()
-        loss = dp.global_loss(nll, n_tok, aux_mean, targets.shape[0], self.weight_target_loss, counts)
-        grads = torch.autograd.grad(loss, self._present)
-        flat_grad = self._flat_gradient(grads)
+        aux_mean = model.get_auxiliary_loss(aux, target_positions) if use_aux else None
         if self.distributed:
-            dp.allreduce_flat_gradient(flat_grad, self.group)
+            if counts_work is not None:
+                counts_work.wait()
+            loss = dp.sum_loss(nll, n_tok, aux_mean, targets.shape[0], self.weight_target_loss, global_counts)
+        else:
+            loss = dp.global_loss(nll, aux_mean, self.weight_target_loss)
+        ops.set_flat_grad_target(self.flat_grad)
+        try:
+            grads = torch.autograd.grad(loss, self._present)
+        finally:
+            ops.set_flat_grad_target(None)
+        flat_grad = self._flat_gradient(grads)
+        denom = None
+        if self.distributed:
+            if flat_grad is not self.flat_grad:
+                flat_grad[n:n + 2].copy_(self.flat_grad[n:n + 2])
+            dp.allreduce_flat_gradient(flat_grad, self.group)     # the single collective of the step
+            denom = flat_grad[n:n + 1]                            # global token count, still on the device
         lr = self.current_lr()
         self.step_count += 1
-        ops.adam_step(self.flat_param, flat_grad, self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1],
-                      self.eps, self.step_count)
+        ops.adam_step(self.flat_param, flat_grad[:n], self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1],
+                      self.eps, self.step_count, grad_denom=denom)
         model.update_state(is_best=False)
         self.last_logp, self.last_aux = logp.detach(), aux
-        return loss.detach()
+        self.last_flat_grad = flat_grad
+        return loss.detach() / denom[0] if denom is not None else loss.detach()
 
     # ---- torch.optim.Adam-compatible state, so checkpoints interoperate with the reference -------
     def state_dict(self) -> dict:
