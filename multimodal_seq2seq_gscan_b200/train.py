@@ -9,12 +9,13 @@
   launch - the reference decodes one example at a time and refuses ``test_batch_size > 1``;
 * data parallelism (new): under ``torchrun`` every rank builds the same shuffled order (numpy seeded with
   ``seed``; the reference leaves it unseeded, train.py:27 vs gSCAN_dataset.py:179) and takes its contiguous
-  shard of every global batch; gradients are summed by one all-reduce per step (``dp.py``).
+  shard of every global batch; gradients and loss normalisers are summed by ONE all-reduce per step (``dp.py``).
 """
 from __future__ import annotations
 
 import logging
 import os
+import random
 
 import numpy as np
 import torch
@@ -50,6 +51,7 @@ def train(data_path: str, data_directory: str, generate_vocabularies: bool, inpu
 
     torch.manual_seed(seed)
     np.random.seed(seed)       # identical shuffles on every rank
+    random.seed(seed)          # ... and the same k-shot examples moved into train / dev (dataset.py uses random.sample)
 
     logger.info("Loading Training set...")
     training_set = GroundedScanDataset(data_path, data_directory, split="train",
@@ -108,20 +110,21 @@ def train(data_path: str, data_directory: str, generate_vocabularies: bool, inpu
         for (input_batch, input_lengths, _, situation_batch, _, target_batch,
              target_lengths, agent_positions, target_positions) in training_set.get_data_iterator(
                 batch_size=training_batch_size):
+            global_counts = None
             if distributed:
-                # this rank's contiguous shard of the global batch.  Commands are cut to the shard's own maximal
-                # length (masked attention: no effect); targets too unless the auxiliary task is on, whose scores
-                # sum the visual attention over EVERY padded step of the global batch (trap A.4-2)
-                lo, hi = dp.shard_bounds(input_batch.shape[0], rank, world)
-                if hi <= lo:
-                    raise ValueError("global batch smaller than the number of ranks")
-                input_lengths, target_lengths = input_lengths[lo:hi], target_lengths[lo:hi]
-                input_batch = input_batch[lo:hi, :int(input_lengths.max())]
-                target_batch = target_batch[lo:hi] if auxiliary_task else target_batch[lo:hi, :int(target_lengths.max())]
-                situation_batch, target_positions = situation_batch[lo:hi], target_positions[lo:hi]
+                # this rank's contiguous shard of the global batch (every rank holds the same global batch, so the
+                # global loss normalisers are known without communication); a batch with fewer examples than ranks -
+                # the ragged tail of an epoch - is skipped by EVERY rank, so nobody waits in a collective alone
+                sharded = dp.shard_batch((input_batch, input_lengths, None, situation_batch, None, target_batch,
+                                          target_lengths, agent_positions, target_positions), rank, world,
+                                         auxiliary_task)
+                if sharded is None:
+                    continue
+                (input_batch, input_lengths, _, situation_batch, _, target_batch, target_lengths, agent_positions,
+                 target_positions), global_counts = sharded
             is_best = False
             loss = trainer.train_step(input_batch, input_lengths, situation_batch, target_batch, target_lengths,
-                                      target_positions if auxiliary_task else None)
+                                      target_positions if auxiliary_task else None, global_counts=global_counts)
             last_loss = loss
 
             if training_iteration % print_every == 0:

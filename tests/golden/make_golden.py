@@ -148,9 +148,70 @@ def run_case(Model, predict, sequence_accuracy, name, cfg_name, overrides, batch
     return cfg, batch_kw, out
 
 
+def run_greedy_long(Model, predict):
+    """Round 2: the reference's own ``predict()`` at the FULL decoding length (max_decoding_steps = 120, the value of
+    all_experiments.sh) on the compositional shape with the auxiliary task, float32 as the reference runs it, with
+    the per-step attention weights it returns (predict.py:108-109) - once with the real EOS and once with EOS
+    unreachable (every sequence runs the full 121 steps: the N+1 cap of predict.py:101)."""
+    cfg = dict(O.CONFIGS["comp"])
+    cfg["auxiliary_task"] = True
+    batch_kw = dict(batch_size=4, max_cmd_len=10, min_cmd_len=5, max_tgt_len=12, min_tgt_len=3)
+    # (seed and scale picked so that the four sequences end after 13, 3, 0 and - never - 121 tokens)
+    params = O.synthetic_params(cfg, SEED + 13, scale=3.0, dtype=torch.float32)
+    batch = O.synthetic_batch(cfg, seed=SEED + 14, **batch_kw)
+    model = Model(**O.model_kwargs(cfg))
+    load_params(model, params)
+    model.eval()
+    commands = torch.tensor(batch["commands"])
+    situations = torch.tensor(batch["situations"])
+    targets = torch.tensor(batch["targets"])
+    positions = torch.tensor(batch["target_positions"])
+    B, Ti, M = commands.shape[0], commands.shape[1], cfg["grid_size"] ** 2
+
+    def iterator():
+        for b in range(B):
+            n_in, n_tg = int(batch["cmd_lengths"][b]), int(batch["tgt_lengths"][b])
+            yield (commands[b:b + 1, :n_in], [n_in], [""], situations[b:b + 1], [{}], targets[b:b + 1, :n_tg], [n_tg],
+                   torch.zeros(1, dtype=torch.long), positions[b:b + 1])
+
+    out = {}
+    max_steps = 120
+    for tag, eos in (("eos", 2), ("noeos", -1)):
+        T = max_steps + 1
+        seq = -np.ones((B, T), dtype=np.int64)
+        lens = np.zeros(B, dtype=np.int64)
+        alphas = np.zeros((B, T, Ti), dtype=np.float32)
+        betas = np.zeros((B, T, M), dtype=np.float32)
+        aux_acc = np.zeros(B)
+        with torch.no_grad():
+            for b, (_i, _d, _s, output_sequence, _t, att_cmd, att_sit, acc) in enumerate(
+                    predict(iterator(), model=model, max_decoding_steps=max_steps, pad_idx=0, sos_idx=1, eos_idx=eos)):
+                n = len(output_sequence)
+                seq[b, :n] = output_sequence
+                lens[b] = n
+                assert len(att_cmd) == n and len(att_sit) == n
+                for t in range(n):
+                    a = np.asarray(att_cmd[t], dtype=np.float32).reshape(-1)      # [n_in] of this example
+                    alphas[b, t, :a.size] = a
+                    betas[b, t] = np.asarray(att_sit[t], dtype=np.float32).reshape(-1)
+                aux_acc[b] = float(acc)
+        out[f"{tag}_sequences"], out[f"{tag}_lengths"] = seq, lens
+        out[f"{tag}_alphas"], out[f"{tag}_betas"], out[f"{tag}_aux_accuracy"] = alphas, betas, aux_acc
+    meta = dict(case_name="greedy_long", cfg_name="comp", overrides=repr({"auxiliary_task": True}),
+                batch_kw=repr(batch_kw), dtype="float32", seed=SEED + 13, weight_target_loss=WEIGHT_TARGET_LOSS,
+                param_scale=3.0, max_decoding_steps=max_steps)
+    path = os.path.join(HERE, "greedy_long.npz")
+    np.savez_compressed(path, __meta__=np.array(repr(meta)), **out)
+    print(f"greedy_long: wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB), lengths with EOS "
+          f"{out['eos_lengths'].tolist()}, without {out['noeos_lengths'].tolist()}")
+
+
 def main():
     Model, predict, sequence_accuracy = import_reference()
     torch.manual_seed(0)
+    if "--only-greedy-long" in sys.argv:
+        run_greedy_long(Model, predict)
+        return
     for case in CASES:
         name = case[0]
         cfg, batch_kw, out = run_case(Model, predict, sequence_accuracy, *case)
@@ -167,6 +228,7 @@ def main():
         np.savez_compressed(path, __meta__=np.array(repr(meta)), **store)
         print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.1f} KiB), loss={float(out['loss']):.6f}, "
               f"greedy_len={out['greedy_lengths'].tolist()}")
+    run_greedy_long(Model, predict)
 
 
 if __name__ == "__main__":

@@ -9,6 +9,7 @@ from oracle import gscan_oracle as O
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASE_NAMES = ["tiny_aux", "tiny_nocond", "demo", "demo_f32", "comp_small", "comp_aux", "tlen_small"]
+# (plus "greedy_long": predict() outputs only - sequences and attention weights at max_decoding_steps = 120)
 
 
 def load_case(name, dtype=None):

@@ -197,6 +197,29 @@ def test_greedy_decode_matches_reference_predict(name):
     assert out2["tokens"].cpu().numpy().tolist() == z["greedy_noeos_sequences"].tolist()
 
 
+@pytest.mark.parametrize("tag,eos", [("eos", 2), ("noeos", -1)])
+def test_greedy_decode_full_length_with_attention_matches_reference(tag, eos):
+    """120 decoding steps against the reference's own predict() (golden `greedy_long`, float32): token sequences,
+    lengths, and the attention weights alpha / beta of every kept step (predict.py:108-109) to 2e-5."""
+    cfg, meta, params, batch, z = load_case("greedy_long", dtype=torch.float32)
+    model = build_model(cfg, params, train=False)
+    d = to_dev(batch)
+    N = int(meta["max_decoding_steps"])
+    out = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], N, 1, eos, return_attention=True)
+    toks, lens = out["tokens"].cpu().numpy(), out["lengths"].cpu().numpy()
+    assert lens.tolist() == z[f"{tag}_lengths"].tolist()
+    al = out["attention_weights_commands"].cpu().numpy()
+    be = out["attention_weights_situations"].cpu().numpy()
+    for b in range(len(lens)):
+        n, n_in = int(lens[b]), int(batch["cmd_lengths"][b])
+        assert toks[b, :n].tolist() == z[f"{tag}_sequences"][b, :n].tolist()
+        if n:
+            np.testing.assert_allclose(al[b, :n, :n_in], z[f"{tag}_alphas"][b, :n, :n_in], rtol=0, atol=2e-5)
+            np.testing.assert_allclose(be[b, :n], z[f"{tag}_betas"][b, :n], rtol=0, atol=2e-5)
+    pred = out["aux_logp"].argmax(dim=1).cpu().numpy()
+    np.testing.assert_allclose(100.0 * (pred == batch["target_positions"]), z[f"{tag}_aux_accuracy"])
+
+
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_batched_predict_and_evaluate_match_reference(name):
     """predict() / evaluate() of the package over ragged batches give, per example, what the reference's
@@ -386,12 +409,13 @@ def test_full_size_greedy_decode_properties():
     assert ((lens >= 0) & (lens <= 121)).all()
     for b in range(200):
         assert (toks[b, :lens[b]] != 2).all() and (toks[b, :lens[b]] >= 0).all()
-    # oracle on a sample of examples
-    idx = [0, 1, 17, 63, 199]
-    seqs, *_ = O.greedy_decode(params, torch.tensor(batch["commands"][idx]), batch["cmd_lengths"][idx],
-                               torch.tensor(batch["situations"][idx]), 120)
-    for k, b in enumerate(idx):
-        assert toks[b, :lens[b]].tolist() == seqs[k]
+    # the oracle on ALL 200 examples (float64: a near-tie in the argmax would show up as a token difference)
+    p64 = {k: v.double() for k, v in params.items()}
+    seqs, *_ = O.greedy_decode(p64, torch.tensor(batch["commands"]), batch["cmd_lengths"],
+                               torch.tensor(batch["situations"]).double(), 120)
+    assert lens.tolist() == [len(s) for s in seqs]
+    for b in range(200):
+        assert toks[b, :lens[b]].tolist() == seqs[b], b
     # singles == batched
     for b in (3, 150):
         n = int(batch["cmd_lengths"][b])
@@ -401,6 +425,10 @@ def test_full_size_greedy_decode_properties():
         assert int(o1["lengths"][0]) == lens[b]
     noeos = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], 120, 1, -1)
     assert (noeos["lengths"].cpu().numpy() == 121).all() and (noeos["steps"].cpu().numpy() == 121).all()
+    # ... and the worst case of the bench (EOS unreachable, 200 x 121 steps) token for token against the oracle
+    seqs_noeos, *_ = O.greedy_decode(p64, torch.tensor(batch["commands"]), batch["cmd_lengths"],
+                                     torch.tensor(batch["situations"]).double(), 120, eos_idx=-1)
+    assert noeos["tokens"].cpu().numpy().tolist() == seqs_noeos
     short = model.greedy_decode(d["commands"], batch["cmd_lengths"], d["situations"], 9, 1, -1)
     assert torch.equal(short["tokens"], noeos["tokens"][:, :10])
 

@@ -99,3 +99,24 @@ def test_sequence_accuracy_edge_cases():
     assert O.sequence_accuracy([3, 4], [3, 4]) == 100.0
     assert O.sequence_accuracy([3, 4, 5], [3, 4]) == pytest.approx(200.0 / 3)
     assert O.sequence_accuracy([0], [3]) == 0.0
+
+
+@pytest.mark.parametrize("tag,eos", [("eos", 2), ("noeos", -1)])
+def test_greedy_decode_full_length_with_attention(tag, eos):
+    """Round 2 golden: the reference's predict() at max_decoding_steps = 120 (float32), sequences AND the per-step
+    attention weights it returns (predict.py:108-109); lengths 13 / 3 / 0 / 121 with the real EOS, 121 everywhere
+    without."""
+    cfg, meta, params, batch, z = load_case("greedy_long")
+    N = int(meta["max_decoding_steps"])
+    seqs, alphas, betas, beta_sum = O.greedy_decode(params, torch.tensor(batch["commands"]), batch["cmd_lengths"],
+                                                    torch.tensor(batch["situations"]), N, eos_idx=eos)
+    assert [len(s) for s in seqs] == z[f"{tag}_lengths"].tolist()
+    for b, s in enumerate(seqs):
+        n = len(s)
+        assert s == z[f"{tag}_sequences"][b, :n].tolist()
+        n_in = int(batch["cmd_lengths"][b])
+        if n:
+            np.testing.assert_allclose(np.stack(alphas[b]), z[f"{tag}_alphas"][b, :n, :n_in], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(np.stack(betas[b]), z[f"{tag}_betas"][b, :n], rtol=0, atol=2e-6)
+    pred = beta_sum.argmax(dim=1).numpy()
+    np.testing.assert_allclose(100.0 * (pred == batch["target_positions"]), z[f"{tag}_aux_accuracy"])
