@@ -11,7 +11,13 @@
  *     allocates nothing: all memory (outputs, workspace) is provided by the caller;
  *   - all floating point is IEEE fp32 (the reference's dtype); tokens are int64 as in the
  *     reference's LongTensors; lengths are int32 on the device (the reference passes host lists);
- *   - re-entrant per device/stream as long as workspaces are distinct.
+ *   - threading: ONE host thread per device at a time.  gscan_forward / gscan_backward / gscan_greedy_decode fork onto
+ *     library-owned helper streams (one set per device) and join back into the caller's stream before returning, so a
+ *     call looks like ordinary work on `stream`; those helper streams, the stage-timing events, the cached TMA
+ *     descriptors and the SM budgets of the persistent GEMMs are per-device library state without locks.  Calls for
+ *     DIFFERENT devices may run concurrently from different threads (all caches are keyed by device); two threads
+ *     driving the same device must serialise their calls.  This matches the reference, which is single-threaded
+ *     and uses the default stream (SURVEY.md 8(b) "Threading").
  *
  * Parameter table: `params` / `grads` are host arrays of GSCAN_NUM_PARAMS device pointers in
  * model.parameters() order (= Adam state order), indexed by the GSCAN_P_* enum.

@@ -77,6 +77,7 @@ struct DecBwd3P {
   long long* timeline;
   // progress signals: every CTA adds 1 to progress[k] once all its global stores of the steps t >= t_signal[k] are visible
   // (the host lets work on those rows start in the shadow of the rest of the sweep: cuStreamWaitValue32)
+  const unsigned int* fwd_tag;   // workspace word the forward call set to the sweep version it ran (3 = decoder_v3.cuh), or null
   unsigned int* progress;   // [n_signals] words, zeroed by the host
   int n_signals;
   int t_signal[4];          // descending
@@ -149,6 +150,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
   for (int d = 0; d < kC; ++d) rb[d] = mapa_u32(smem_base, (uint32_t)d);
   const uint32_t rb_u = mapa_u32(smem_base, (uint32_t)(lane & 3)), rb_4 = rb[4];
 
+  // The saved activations and P = W K^T must come from the v3 forward sweep of the same workspace: anything else
+  // (a forward call that fell back to another kernel, a foreign workspace) stops the kernel with an error
+  // instead of producing gradients from uninitialised memory.
+  if (p.fwd_tag != nullptr && tid == 0 && __ldg(p.fwd_tag) != 0x03030303u) __trap();   // cudaMemsetAsync(.., 3, 4)
   // ---- one-time staging ------------------------------------------------------------------------------
   // transposed weight slices as mma A fragments: unit (tile, step) holds rows h = 16*tile + {g, g+8},
   // columns k = 8*step + {2t, 2t+1} of A[h][k] = W[input k of this CTA's slice][output h]

@@ -582,12 +582,11 @@ inline bool eligible(const float* A, long a_rs, long a_cs, const float* B, long 
 }
 
 inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
+  static int per_device[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  int& n = per_device[dev];
+  if (!n && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
   return n;
 }
 
@@ -607,7 +606,10 @@ inline int usable_sms() {
 
 template <bool AK, bool BKM>
 inline int launch_t(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, dim3 grid, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_d[16] = {};   // per device: the attribute is a per-device setting
+  int dev_ = 0;
+  if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 16) return GSCAN_E_UNSUPPORTED;
+  bool& configured = configured_d[dev_];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<AK, BKM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
@@ -724,7 +726,10 @@ inline int launch_group_tn(const GroupProblem* probs, int n, int R, cudaStream_t
   } else if (p.ksplit == 1) {
     p.accumulate = 1;   // destinations hold the other partial sums
   }
-  static bool configured = false;
+  static bool configured_d[16] = {};   // per device: the attribute is a per-device setting
+  int dev_ = 0;
+  if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 16) return GSCAN_E_UNSUPPORTED;
+  bool& configured = configured_d[dev_];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_group_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;

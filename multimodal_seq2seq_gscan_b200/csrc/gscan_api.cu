@@ -35,12 +35,11 @@ namespace {
 constexpr size_t kMaxSmemBytes = 227 * 1024;
 
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
+  static int per_device[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return 148;
+  int& n = per_device[dev];
+  if (n == 0 && (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)) n = 148;
   return n;
 }
 
@@ -143,6 +142,7 @@ struct Layout {
   size_t WA_t, WB_t, WC_t, WD_t, WhhE_t[2];
   size_t WA2, WC2, WD2, PT;   // cluster-resident decoder sweep (decoder_cluster.cuh)
   size_t U, Xe, Cs, gates, alpha, beta, Qp, qT, qV, beta_sum, aux_logp, pre, logp;
+  size_t tag;                  // which decoder sweep the forward call ran (checked by the v3 backward kernel)
   // backward scratch
   size_t dlogits, dpre, dU, dgates, dd, dqV, dqT, dKT, dKV, dh0, dbeta_aux, dfeat, dconv, dWt_cnn;
   size_t denc_out, dh_enc, dpre0, dga[2], hprev[2], denc_x, dvec;
@@ -191,6 +191,7 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
   L.aux_logp = L.take(B * M);
   L.pre = L.take(Tt * B * H);
   L.logp = L.take(B * Tt * V);
+  L.tag = L.take(4);
   if (with_backward) {
     L.dlogits = L.take(Tt * B * V);
     L.dpre = L.take(Tt * B * H);
@@ -638,8 +639,14 @@ int launch_dec_fwd_cluster(const gscan_dims& d, const float* const* P, float* ws
 // ---- register-resident cluster sweep (v3, decoder_v3.cuh): H = 100, 6x6 grid only ---------------------
 template <bool COND, bool GREEDY, bool TL = false>
 int v3_fwd_prepare(size_t bytes) {
-  static bool done = false, ok = false;
-  static size_t done_bytes = 0;
+  // per device: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting
+  static bool done_d[16] = {}, ok_d[16] = {};
+  static size_t done_bytes_d[16] = {};
+  int dev_ = 0;
+  if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 16) return GSCAN_E_UNSUPPORTED;
+  bool& done = done_d[dev_];
+  bool& ok = ok_d[dev_];
+  size_t& done_bytes = done_bytes_d[dev_];
   if (done && bytes <= done_bytes) return ok ? 0 : GSCAN_E_UNSUPPORTED;
   auto kern = v3::dec_fwd_v3_kernel<COND, GREEDY, TL>;
   ok = false;
@@ -737,8 +744,14 @@ int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, con
 
 template <bool COND, bool TL = false>
 int v3_bwd_prepare(size_t bytes) {
-  static bool done = false, ok = false;
-  static size_t done_bytes = 0;
+  // per device: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting
+  static bool done_d[16] = {}, ok_d[16] = {};
+  static size_t done_bytes_d[16] = {};
+  int dev_ = 0;
+  if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 16) return GSCAN_E_UNSUPPORTED;
+  bool& done = done_d[dev_];
+  bool& ok = ok_d[dev_];
+  size_t& done_bytes = done_bytes_d[dev_];
   if (done && bytes <= done_bytes) return ok ? 0 : GSCAN_E_UNSUPPORTED;
   auto kern = v3::dec_bwd_v3_kernel<COND, TL>;
   ok = false;
@@ -967,6 +980,8 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   } else {
     TRY(launch_dec_fwd(*d, p, false, st));
   }
+  // every byte of the tag word = version of the sweep that produced the saved activations of this workspace
+  TRYCUDA(cudaMemsetAsync(ws + L.tag, v3_done ? 3 : (cc.C ? 2 : 1), sizeof(unsigned int), st));
   prof_mark(3, st);
   chain_mark("m:sweep_done", st);
   // output projection for all steps at once, then log-softmax.  (Chunks of it in the shadow of the forward sweep, the
@@ -1136,6 +1151,7 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       b3.n_signals = n_cut;
       for (int k = 0; k < n_cut; ++k) b3.t_signal[k] = t_cut[k];
     }
+    b3.fwd_tag = reinterpret_cast<const unsigned int*>(ws + L.tag);
     b3.B = B; b3.T = Tt; b3.Ti = Ti;
     b3.W_ih = bp.W_ih; b3.W_hh = bp.W_hh; b3.W_qV = bp.W_qV; b3.W_c = bp.W_c; b3.W_qT = bp.W_qT;
     b3.PT = ws + L.PT;   // computed by the forward call on this workspace
@@ -1157,7 +1173,10 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
       for (int k = 0; k < n_cut; ++k) {
         if (stream_wait_value_fn()((CUstream)sh, (CUdeviceptr)(progress + k), (cuuint32_t)sweep_ctas, 0u /* GEQ */) !=
             CUDA_SUCCESS) {
-          if (k > 0) return GSCAN_E_UNSUPPORTED;   // (a driver that accepted the first wait accepts the next)
+          if (k > 0) {   // (a driver that accepted the first wait accepts the next.)  Nothing of this call may stay in
+            join_side(S, 2, st);   // flight on a helper stream when it returns: the caller owns the workspace again
+            return GSCAN_E_UNSUPPORTED;
+          }
           shadow = false;                          // stream memory operations unavailable: everything after the sweep
           TRY(join_side(S, 2, st));
           break;

@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(1024) nll_forward_kernel(const float* __restri
       y[u] = pad;
       if (r < R) {
         int b = r / T, t = r - (long)b * T;
-        if (t + shift < T) y[u] = tgt[(long)b * T + t + shift];
+        // beyond the shifted sequence the reference appends a literal 0 (remove_start_of_sequence, model.py:108-115):
+        // ignored when pad == 0 (the gSCAN vocabularies), scored as class 0 otherwise - as NLLLoss(ignore_index) does
+        y[u] = (t + shift < T) ? tgt[(long)b * T + t + shift] : (shift > 0 ? 0 : pad);
       }
     }
     float lp[kU];
@@ -380,8 +382,8 @@ __global__ void nll_backward_kernel(const long long* __restrict__ tgt, int B, in
   long r = idx / V;
   int b = r / T, t = r - (long)b * T;
   float g = 0.f;
-  if (t + shift < T) {
-    long long y = tgt[(long)b * T + t + shift];
+  {
+    const long long y = (t + shift < T) ? tgt[(long)b * T + t + shift] : (shift > 0 ? 0 : pad);   // see nll_forward_kernel
     if (y != pad && y == v) g = -__ldg(d_loss) / __ldg(loss_out + 1);
   }
   d_logp[idx] = g;
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(256) metrics_kernel(const float* __restrict__ 
   if (b >= B) return;
   int match = 0, total = 0;
   for (int t = lane; t < T; t += 32) {
-    long long y = (t + 1 < T) ? tgt[(long)b * T + t + 1] : pad;
+    long long y = (t + 1 < T) ? tgt[(long)b * T + t + 1] : 0;   // the appended literal 0 (model.py:108-115,121)
     if (y == pad) continue;
     const float* lp = logp + ((long)b * T + t) * V;
     int arg = 0;

@@ -56,7 +56,8 @@ def shard_batch(batch: Sequence, rank: int, world: int, auxiliary_task: bool):
     Commands are cut to the shard's own maximal length (masked attention: no effect on the result);
     targets too unless the auxiliary task is on, whose scores sum the visual attention over EVERY
     padded step of the global batch (SURVEY.md trap A.4-2).  Also returns the global counts
-    ``(N_tok, B_all)`` as Python numbers, computed from the global target lengths every rank holds."""
+    ``(N_tok, B_all)`` as Python numbers, computed from the global target lengths every rank holds (pad index 0,
+    as in every gSCAN vocabulary: the scored targets of an example are its tokens after SOS)."""
     (input_batch, input_lengths, derivation, situation_batch, situation_repr, target_batch, target_lengths,
      agent_positions, target_positions) = batch
     n = int(input_batch.shape[0])
@@ -83,7 +84,10 @@ def local_counts(targets: torch.Tensor, pad_idx: int) -> torch.Tensor:
     key = (targets.device, int(targets.shape[0]))
     if key not in _BATCH_CONST:
         _BATCH_CONST[key] = torch.full((), float(targets.shape[0]), dtype=torch.float32, device=targets.device)
-    return torch.stack(((targets[:, 1:] != pad_idx).sum(dtype=torch.float32), _BATCH_CONST[key]))
+    n_tok = (targets[:, 1:] != pad_idx).sum(dtype=torch.float32)
+    if pad_idx != 0:      # the literal 0 appended behind every shifted sequence is scored then (model.py:108-115)
+        n_tok = n_tok + _BATCH_CONST[key]
+    return torch.stack((n_tok, _BATCH_CONST[key]))
 
 
 _BATCH_CONST: dict = {}

@@ -241,7 +241,9 @@ class Model(nn.Module):
         return 100. * equal / len(targets)
 
     def get_loss(self, target_scores: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        """Mean NLL of [B,Tt,V] log-probabilities against targets shifted left by one, ignoring pad."""
+        """Mean NLL of [B,Tt,V] log-probabilities against targets shifted left by one, ignoring pad.  The position
+        behind the last target holds the literal 0 the reference appends (model.py:108-115): ignored when
+        target_pad_idx == 0 (the gSCAN vocabularies), scored as class 0 otherwise - the kernels do the same."""
         return ops.NLLLoss.apply(target_scores, targets, self.target_pad_idx, 1)[0]
 
     def get_auxiliary_loss(self, auxiliary_scores_target: torch.Tensor, target_target_positions: torch.Tensor):
@@ -310,6 +312,11 @@ class Model(nn.Module):
         ``steps``, ``beta_sum`` [B, G*G], ``aux_logp`` (if the auxiliary task is on) and, on request,
         the per-step attention weights."""
         G = situations_input.shape[1]
+        if self._static_cfg["V"] > 32:
+            raise NotImplementedError(
+                "batched greedy decoding keeps the logits of one example in the registers of one lane: target "
+                "vocabularies above 32 entries (gSCAN has 8-9) are not supported by gscan_greedy_decode; "
+                "use the step-wise encode_input / decode_input loop of predict.py for such a model")
         return ops.greedy_decode(self._cfg(G), self._param_list(), commands_input, commands_lengths,
                                  situations_input, max_decoding_steps, sos_idx, eos_idx,
                                  return_attention=return_attention, want_aux=bool(self.auxiliary_task))
