@@ -15,7 +15,9 @@ from ctypes import POINTER, c_float, c_int32, c_int64, c_size_t, c_void_p
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
 LIB_DIR = os.path.join(PKG_DIR, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libgscan_b200.so")
+# GSCAN_LIB=<path> loads another build of the library (A/B experiments with tools/exp_build.sh); the default is the
+# in-tree lib/libgscan_b200.so that build() produces
+LIB_PATH = os.environ.get("GSCAN_LIB") or os.path.join(LIB_DIR, "libgscan_b200.so")
 INCLUDE_DIR = os.path.join(os.path.dirname(PKG_DIR), "include")
 
 NUM_PARAMS = 32

@@ -26,6 +26,7 @@ constexpr int kXS = 104;   // row stride of the gathered activation vectors (13 
 constexpr int kKSteps = 13;
 constexpr int kGS = 84;    // row stride of the gate pre-activation scratch (bank spread)
 constexpr int kMaxTi = 16;
+constexpr int kTlStamps = 24;   // phase stamps per step of the instrumented (TL) instantiations: 0-15 phases, 16+ sub-phases
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -174,7 +175,7 @@ struct DecFwd3P {
   const float *h_init, *c_init;   // [B][H]
   const float* Xe;                // [T][B][4H]
   float *U, *Cs, *gates, *alpha, *beta, *Qp, *qT, *qV, *beta_sum;   // saved activations (recurrent.cuh DecFwdP)
-  long long* timeline;   // debug: [T][16] clock64 stamps of CTA 0, else null
+  long long* timeline;   // debug: [T][16 stamps][16 warps] clock64 stamps of CTA 0 (lane 0 of every warp), else null
   // greedy decoding (predict.py:97-117); tables as in recurrent.cuh DecFwdP
   const float *XeTab, *OutE, *Wo_t;
   int V, Vp, sos, eos;
@@ -188,7 +189,8 @@ struct DecFwd3P {
 #define GSCAN3_STAMP(k)                                                                              \
   do {                                                                                               \
     if constexpr (TL) {                                                                              \
-      if (p.timeline && blockIdx.x == 0 && threadIdx.x == 0) p.timeline[t * 16 + (k)] = clock64();   \
+      if (p.timeline && blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                  \
+        p.timeline[((size_t)t * kTlStamps + (k)) * 16 + (threadIdx.x >> 5)] = clock64();             \
     }                                                                                                \
   } while (0)
 
@@ -302,6 +304,119 @@ __device__ __forceinline__ void partial_scores(const float* __restrict__ q_s, co
   }
 }
 
+// Round 2: LANES threads per (example, key) pair, each covering 20 / LANES contiguous hidden units with vector loads
+// (rows of K are 80 bytes: 16-byte aligned; lanes at a stride of 20 floats hit all 32 banks once per quarter-warp).
+// The 4-lane form above spends ~145 warp-instructions per 32 items on scalar loads, index arithmetic and two
+// shuffles - the visual scores alone were 29 % of all instructions issued per decoder step (ncu, profiles/r02_*);
+// one thread per pair issues ~2.5x fewer and needs no shuffle.  LANES = 2 halves the dependent chain for the short
+// text attention (8 x Ti pairs), where latency, not issue slots, is what counts.
+template <int NKEYS_CT, int LANES>
+__device__ __forceinline__ void partial_scores_vec(const float* __restrict__ q_s, const float* __restrict__ K_s,
+                                                   const float* __restrict__ v_s, int nkeys, int xoff_floats, int rank,
+                                                   uint32_t rb_k, uint32_t rb_4, uint32_t bar_off) {
+  // rb_k: shared-memory window of CTA (lane & 3) for LANES = 1, of CTA min(lane & 7, 4) for LANES = 2; rb_4: of CTA 4
+  static_assert(LANES == 1 || LANES == 2, "20 hidden units per CTA: 1 x 20 or 2 x 10");
+  const int N = NKEYS_CT > 0 ? NKEYS_CT : nkeys;
+  const int total = kNB * N * LANES;
+  for (int base = (threadIdx.x >> 5) * 32; base < total; base += kThreads) {
+    const int item = base + (threadIdx.x & 31);
+    const int pair = item / LANES, u = item - pair * LANES;
+    float s = 0.f;
+    if (item < total) {
+      const int n = pair / N;
+      float s1 = 0.f;
+      if (LANES == 1) {
+        const float4* kp = reinterpret_cast<const float4*>(K_s + pair * kHS);
+        const float4* qp = reinterpret_cast<const float4*>(q_s + n * kHS);
+        const float4* vp = reinterpret_cast<const float4*>(v_s);
+#pragma unroll
+        for (int i = 0; i < kHS / 4; ++i) {
+          const float4 k = kp[i], q = qp[i], v = vp[i];
+          s = fmaf(v.x, act_tanh(q.x + k.x), s);
+          s1 = fmaf(v.y, act_tanh(q.y + k.y), s1);
+          s = fmaf(v.z, act_tanh(q.z + k.z), s);
+          s1 = fmaf(v.w, act_tanh(q.w + k.w), s1);
+        }
+      } else {
+        const float2* kp = reinterpret_cast<const float2*>(K_s + pair * kHS + 10 * u);
+        const float2* qp = reinterpret_cast<const float2*>(q_s + n * kHS + 10 * u);
+        const float2* vp = reinterpret_cast<const float2*>(v_s + 10 * u);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const float2 k = kp[i], q = qp[i], v = vp[i];
+          s = fmaf(v.x, act_tanh(q.x + k.x), s);
+          s1 = fmaf(v.y, act_tanh(q.y + k.y), s1);
+        }
+      }
+      s += s1;
+    }
+    if (LANES == 2) s += __shfl_xor_sync(0xffffffffu, s, 1);
+    // Four consecutive pairs travel as ONE 16-byte st.async per destination: every st.async is one transaction on the
+    // receiver's mbarrier, and the exchanges of a step are bound by the NUMBER of those, not by their bytes
+    // (kNB * N is a multiple of 4 and the score buffers are 16-byte aligned, so a group is all valid or all padding).
+    const int lane = threadIdx.x & 31;
+    constexpr int G = 4 * LANES;                  // lanes that hold one group of four pair sums
+    const int g0 = lane & ~(G - 1), k = lane & (G - 1);
+    float4 v;
+    v.x = __shfl_sync(0xffffffffu, s, g0);
+    v.y = __shfl_sync(0xffffffffu, s, g0 + LANES);
+    v.z = __shfl_sync(0xffffffffu, s, g0 + 2 * LANES);
+    v.w = __shfl_sync(0xffffffffu, s, g0 + 3 * LANES);
+    if (item < total) {
+      const uint32_t off = (uint32_t)(xoff_floats + rank * kNB * N + (base + g0) / LANES) * 4u;
+      if (LANES == 1) {   // lane k of the group -> CTA k, lane 0 also -> CTA 4
+        st_async_f32x4(rb_k + off, v, rb_k + bar_off);
+        if (k == 0) st_async_f32x4(rb_4 + off, v, rb_4 + bar_off);
+      } else if (k < kC) {   // lanes 0..4 of the group of eight -> CTA 0..4
+        st_async_f32x4(rb_k + off, v, rb_k + bar_off);
+      }
+    }
+  }
+}
+
+// Four lanes per (example, key) pair like partial_scores (the tanh work - 2 MUFU each - stays spread evenly over all 16
+// warps / 4 SFU pipes; one thread per pair puts 3 of the 9 busy warps on one scheduler: measured slower), but lane u
+// covers hidden units {4u .. 4u+3, 16+u}: one 16-byte and one 4-byte load per operand instead of five scalar ones,
+// and four consecutive pair sums leave as ONE 16-byte st.async per destination (lanes 0..4 of each group of 16 lanes
+// -> CTA 0..4): 360 instead of 1440 mbarrier transactions per receiver for the visual scores
+// (tools/ubench_exchange.cu: 1207 -> 899 cycles per exchange).  rb_16 = window of CTA min(lane & 15, 4).
+template <int NKEYS_CT>
+__device__ __forceinline__ void partial_scores_q4(const float* __restrict__ q_s, const float* __restrict__ K_s,
+                                                  const float* __restrict__ v_s, int nkeys, int xoff_floats, int rank,
+                                                  uint32_t rb_16, uint32_t bar_off) {
+  const int lane = threadIdx.x & 31, u = lane & 3;
+  const int N = NKEYS_CT > 0 ? NKEYS_CT : nkeys;
+  const int total = kNB * N * 4;   // a multiple of 32: whole warps
+  const float4 v4 = lds4(v_s + 4 * u);
+  const float v1 = v_s[16 + u];
+  const int g0 = lane & 16, k = lane & 15;
+  for (int base = (threadIdx.x >> 5) * 32; base < total; base += kThreads) {
+    const int pair = (base + lane) >> 2;
+    const int n = pair / N;
+    const float* kp = K_s + pair * kHS;
+    const float* qp = q_s + n * kHS;
+    const float4 k4 = lds4(kp + 4 * u), q4 = lds4(qp + 4 * u);
+    const float k1 = kp[16 + u], q1 = qp[16 + u];
+    float s = v4.x * act_tanh(q4.x + k4.x);
+    float s1 = v4.y * act_tanh(q4.y + k4.y);
+    s = fmaf(v4.z, act_tanh(q4.z + k4.z), s);
+    s1 = fmaf(v4.w, act_tanh(q4.w + k4.w), s1);
+    s = fmaf(v1, act_tanh(q1 + k1), s);
+    s += s1;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    float4 o;
+    o.x = __shfl_sync(0xffffffffu, s, g0);
+    o.y = __shfl_sync(0xffffffffu, s, g0 + 4);
+    o.z = __shfl_sync(0xffffffffu, s, g0 + 8);
+    o.w = __shfl_sync(0xffffffffu, s, g0 + 12);
+    if (k < kC) {
+      const uint32_t off = (uint32_t)(xoff_floats + rank * kNB * N + ((base + g0) >> 2)) * 4u;
+      st_async_f32x4(rb_16 + off, o, rb_16 + bar_off);
+    }
+  }
+}
+
 template <bool COND, bool GREEDY, bool TL = false>
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fwd_v3_kernel(DecFwd3P p) {
   extern __shared__ __align__(16) float smem[];
@@ -349,6 +464,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
 #pragma unroll
   for (int d = 0; d < kC; ++d) rb[d] = mapa_u32(smem_base, (uint32_t)d);
   const uint32_t rb_u = mapa_u32(smem_base, (uint32_t)(lane & 3)), rb_4 = rb[4];
+  const uint32_t rb_8 = mapa_u32(smem_base, (uint32_t)min(lane & 7, kC - 1));
   const uint32_t boff = (uint32_t)L.bars * 4u;
 
   // ---- resident weight fragments; the content depends on the warp's role ---------------------------------
@@ -548,6 +664,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     // ---- stage A: everything that depends only on h_{t-1} ---------------------------------------------
     float o[4] = {0.f, 0.f, 0.f, 0.f};
     if (roleA) mv_tile(whi, wlo_lane, hfull_s + fg * kXS + 2 * ft, o);
+    GSCAN3_STAMP(16);
     if (GREEDY) {
       // The token of the previous step is picked HERE, by the otherwise idle warp 15, while the role-A warps run the
       // mat-vecs on h (which do not depend on the token); only the embedding term added below needs it.
@@ -580,12 +697,14 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
           g_s[n * kGS + lr - 2 * kHS] = o[j] + (GREEDY ? xeTab_s[tok_s[n] * kG4 + lr - 2 * kHS] : xe[j]);
         }
       }
+      GSCAN3_STAMP(17);
       if (!GREEDY && t + 1 < p.T) load_xe(row0 + B);
     }
+    GSCAN3_STAMP(18);
     __syncthreads();
     GSCAN3_STAMP(2);
     // ---- textual attention: partial scores over the local slice, summed over ranks (X1) ---------------
-    partial_scores<0>(qT_s, KT_s, vT_s, Ti, L.xT, rank, rb_u, rb_4, boff + 0u);
+    partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, rb_8, rb_4, boff + 0u);
     GSCAN3_STAMP(3);
     mbar_wait(bar0 + 8u * 0, par);
     GSCAN3_STAMP(4);
@@ -609,6 +728,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
           p.g_alphas[((size_t)(b0 + n) * p.T + t) * Ti + lane] = a;
       }
     }
+    GSCAN3_STAMP(19);
     __syncthreads();
     GSCAN3_STAMP(5);
     // ---- everything linear in c_T through P_j = W K^T_j: q' slice (X3), gate contributions, c_T slice ----
@@ -666,7 +786,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     __syncthreads();
     GSCAN3_STAMP(8);
     // ---- visual attention: partial scores (X4), softmax, c_V slice gathered (X5) -------------------------
-    partial_scores<kM>(qV_s, KV_s, vV_s, kM, L.xV, rank, rb_u, rb_4, boff + 8u * 2);
+    partial_scores_vec<kM, 1>(qV_s, KV_s, vV_s, kM, L.xV, rank, rb_u, rb_4, boff + 8u * 2);
     GSCAN3_STAMP(9);
     mbar_wait(bar0 + 8u * 2, par);
     GSCAN3_STAMP(10);
@@ -701,7 +821,9 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         if (lane < kM - 32) gb[32 + lane] = w1;
       }
     }
+    GSCAN3_STAMP(20);
     __syncthreads();
+    GSCAN3_STAMP(21);
     if (tid < kNB * 5 * 4) {
       // 4 lanes per (example, hidden quad): each sums 9 of the 36 cells, then a butterfly all-reduce
       const int k = tid >> 2, u = tid & 3;
@@ -741,6 +863,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
 #pragma unroll
       for (int j = 0; j < 4; ++j) g_s[(nF + (j & 1)) * kGS + lr0 + 8 * (j >> 1)] += o[j];
     }
+    GSCAN3_STAMP(22);
     __syncthreads();
     GSCAN3_STAMP(13);
     if (tid < kNB * kHS) {
@@ -749,9 +872,17 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       c_reg = fmaf(fg, c_reg, ig * gg);
       const float hn = og * act_tanh(c_reg);
       if (t + 1 < p.T) {
-        const uint32_t off = (uint32_t)(L.hfull + cn * kXS + S0 + chh) * 4u;
-#pragma unroll
-        for (int d = 0; d < kC; ++d) st_async_f32(rb[d] + off, hn, rb[d] + boff + 8u * 4);
+        // four consecutive hidden units of one example (20 per example: a group never straddles two) as one 16-byte store
+        // per destination: lane k of the group -> CTA k, lane 0 also -> CTA 4 (tid < 160 = five full warps)
+        const int g0 = lane & ~3, k = lane & 3;
+        float4 v;
+        v.x = __shfl_sync(0xffffffffu, hn, g0);
+        v.y = __shfl_sync(0xffffffffu, hn, g0 + 1);
+        v.z = __shfl_sync(0xffffffffu, hn, g0 + 2);
+        v.w = __shfl_sync(0xffffffffu, hn, g0 + 3);
+        const uint32_t off = (uint32_t)(L.hfull + cn * kXS + S0 + (chh & ~3)) * 4u;
+        st_async_f32x4(rb_u + off, v, rb_u + boff + 8u * 4);
+        if (k == 0) st_async_f32x4(rb_4 + off, v, rb_4 + boff + 8u * 4);
       }
       if (GREEDY) u_s[cn * 3 * kHS + chh] = hn;
       if (!GREEDY && cn < nb) {

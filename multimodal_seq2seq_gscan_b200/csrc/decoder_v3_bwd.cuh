@@ -24,9 +24,15 @@ constexpr int kTiles = 7;   // ceil(100 / 16) output tiles of the transposed pro
 // weight units (16 rows x 8 columns each) per output tile, in shared memory fragment order
 constexpr int kUcV = 0, kUhh = 10, kUc = 20, kUqT = 23, kUqV = 26, kUnitsPerTile = 29;
 constexpr int kMaxTiB = 16;   // text positions per attention thread: 8 registers
+// Saved activations of a step are staged through shared memory by the two I/O warps (14, 15): one row of kStageRow
+// floats per example, filled with 16-byte coalesced loads one step ahead, double buffered
+//   [gates i f g o: 80 | c_{t-1}: 20 | dU_h: 20 | dU_cT: 20 | dU_cV: 20 | q': 20 | q_V: 20 | q_T: 20 | beta: 36]
+constexpr int kStageRow = 256, kStageQ = kStageRow / 4;
+constexpr int kSgC = 80, kSgDUh = 100, kSgDUcT = 120, kSgDUcV = 140, kSgQp = 160, kSgQV = 180, kSgQT = 200, kSgBeta = 220;
+constexpr int kIoWarp0 = 14, kIoThreads = 64;
 
 struct BwdSmem {
-  int W, KV, KT, P, da, dqV, dd, dqT, dUcT, dhpart, dcV, xcV, xbe, xqp, xal, xdh, drV, drT, a1, vT, vV, len, bars, total;
+  int W, KV, KT, P, da, dqV, dd, dqT, dUcT, dhpart, dcV, xcV, xbe, xqp, xal, xdh, drV, drT, a1, vT, vV, len, bars, stage, total;
 };
 __host__ __device__ inline BwdSmem bwd_smem(int Ti, int cond) {
   BwdSmem s{};
@@ -56,6 +62,7 @@ __host__ __device__ inline BwdSmem bwd_smem(int Ti, int cond) {
   s.vV = take(kHS);
   s.len = take(kNB);
   s.bars = take(16);
+  s.stage = take(2 * kNB * kStageRow);
   s.total = o;
   return s;
 }
@@ -200,6 +207,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     for (int i = tid; i < kNB * kDaS; i += kThreads) da_s[i] = 0.f;
     for (int i = tid; i < kNB * kVs; i += kThreads) { dqV_s[i] = 0.f; dd_s[i] = 0.f; dqT_s[i] = 0.f; }
     for (int i = tid; i < kNB * kH; i += kThreads) dhpart_s[i] = 0.f;
+    for (int i = tid; i < 2 * kNB * kStageRow; i += kThreads) smem[L.stage + i] = 0.f;   // rows of absent examples stay zero
     if (tid < kHS) {
       vT_s[tid] = __ldg(p.vT + S0 + tid);
       vV_s[tid] = __ldg(p.vV + S0 + tid);
@@ -230,38 +238,64 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
 
   // recurrent state of the cell threads
   float dc_carry = 0.f, dh_extra = 0.f;
-  // prefetched saved activations of the step about to be processed
-  float c_gi = 0.f, c_gf = 0.f, c_gg = 0.f, c_go = 0.f, c_cprev = 0.f, c_cnew = 0.f, c_dUh = 0.f, c_dUcT = 0.f,
-        c_dUcV = 0.f, c_qp = 0.f;
-  float a_qv = 0.f, a_qt = 0.f;
-  float s_b0 = 0.f, s_b1 = 0.f, s_al = 0.f, s_aux0 = 0.f, s_aux1 = 0.f;
-  auto load_cell = [&](int t, bool first) {
-    if (!cn_ok) return;
-    const size_t row = (size_t)t * B + b0 + cn;
-    const float* gp = p.gates + row * H4 + S0 + chh;
-    c_gi = __ldg(gp); c_gf = __ldg(gp + kH); c_gg = __ldg(gp + 2 * kH); c_go = __ldg(gp + 3 * kH);
-    c_cnew = first ? __ldg(p.Cs + (row + B) * kH + S0 + chh) : c_cprev;
-    c_cprev = __ldg(p.Cs + row * kH + S0 + chh);
-    const float* du = p.dU + row * H4 + S0 + chh;
-    c_dUh = __ldg(du + kH); c_dUcT = __ldg(du + 2 * kH); c_dUcV = __ldg(du + 3 * kH);
-    if (COND) c_qp = __ldg(p.Qp + row * kH + S0 + chh);
+  // Round 2: the saved activations of a step reach their consumers through shared memory.  In round 1 every cell /
+  // attention / softmax thread fetched its own 4-byte words one step ahead (9 + 2 + 3 scattered loads per thread and
+  // step) and stored its own gradients (7 scattered stores): taking exactly these loads and stores out of the kernel
+  // shortened the sweep from 1.12 to 0.80 ms (experiment) - the address arithmetic and the LSU slots
+  // sit on the critical path of phases that are bound by issue and latency.  Now warps 14 and 15, idle for most of
+  // a step, move the same bytes with 16-byte coalesced accesses.
+  float* stage_s = smem + L.stage;
+  const bool ioT = warp >= kIoWarp0;
+  const int io = tid - kIoWarp0 * 32;          // 0..63 for the I/O threads: float4 column of the staging row
+  const float* io_src = nullptr;               // source of that column in row t*B + b (global), and its row stride
+  size_t io_stride = 0;
+  if (ioT) {
+    const int q = io;
+    if (q < 20) { io_src = p.gates + (q / 5) * kH + S0 + 4 * (q % 5); io_stride = H4; }
+    else if (q < 25) { io_src = p.Cs + S0 + 4 * (q - 20); io_stride = kH; }
+    else if (q < 40) { io_src = p.dU + (1 + (q - 25) / 5) * kH + S0 + 4 * ((q - 25) % 5); io_stride = H4; }
+    else if (q < 45) { io_src = COND ? p.Qp + S0 + 4 * (q - 40) : nullptr; io_stride = kH; }
+    else if (q < 50) { io_src = p.qV + S0 + 4 * (q - 45); io_stride = kH; }
+    else if (q < 55) { io_src = p.qT + S0 + 4 * (q - 50); io_stride = kH; }
+    else { io_src = p.beta + 4 * (q - 55); io_stride = kM; }
+  }
+  // 16-byte asynchronous copies global -> shared (LDGSTS: no registers held while the data is in flight); io_commit
+  // waits for them, the block barrier that follows publishes the buffer
+  auto io_issue = [&](int t, int buf) {
+    if (!ioT || io_src == nullptr) return;
+#pragma unroll
+    for (int n = 0; n < kNB; ++n) {
+      if (n < nb) {
+        const uint32_t dst = smem_u32(stage_s + (buf * kNB + n) * kStageRow + 4 * io);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(io_src + ((size_t)t * B + b0 + n) * io_stride) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  auto load_att = [&](int t) {
-    if (!an_ok) return;
-    const size_t row = (size_t)t * B + b0 + an;
-    a_qv = __ldg(p.qV + row * kH + S0 + ah);
-    a_qt = __ldg(p.qT + row * kH + S0 + ah);
+  auto io_commit = [&]() {
+    if (ioT) asm volatile("cp.async.wait_group 0;" ::: "memory");
   };
+  // rows [r_lo, ...) of a [kNB][stride] shared-memory array, `nq` float4 per row, to global rows (row0 + n) * gstride + goff(q)
+  auto io_store = [&](const float* src_s, int sstride, int nq, float* dst, size_t row0_, int gstride, bool gate_cols) {
+    if (!ioT) return;
+    for (int f = io; f < kNB * nq; f += kIoThreads) {
+      const int n = f / nq, q = f - n * nq;
+      if (n < nb) {
+        const int gcol = gate_cols ? (q / 5) * kH + 4 * (q % 5) : 4 * q;
+        *reinterpret_cast<float4*>(dst + (row0_ + n) * gstride + S0 + gcol) = lds4(src_s + n * sstride + 4 * q);
+      }
+    }
+  };
+  float c_cnew = 0.f, s_al = 0.f, s_aux0 = 0.f, s_aux1 = 0.f;
+  if (cn_ok) c_cnew = __ldg(p.Cs + ((size_t)p.T * B + b0 + cn) * kH + S0 + chh);   // c_{T-1}: row group T of Cs
   auto load_soft = [&](int t) {
     if (warp >= nb) return;
-    const size_t row = (size_t)t * B + b0 + warp;
-    s_b0 = __ldg(p.beta + row * kM + lane);
-    s_b1 = (lane < kM - 32) ? __ldg(p.beta + row * kM + 32 + lane) : 0.f;
-    s_al = (lane < Ti) ? __ldg(p.alpha + row * Ti + lane) : 0.f;
+    s_al = (lane < Ti) ? __ldg(p.alpha + ((size_t)t * B + b0 + warp) * Ti + lane) : 0.f;
   };
-  load_cell(p.T - 1, true);
-  load_att(p.T - 1);
   load_soft(p.T - 1);
+  __syncthreads();   // the staging buffers have been zeroed
+  io_issue(p.T - 1, 0);
+  io_commit();
   if (p.dbeta_aux && warp < nb) {
     s_aux0 = __ldg(p.dbeta_aux + (size_t)(b0 + warp) * kM + lane);
     s_aux1 = (lane < kM - 32) ? __ldg(p.dbeta_aux + (size_t)(b0 + warp) * kM + 32 + lane) : 0.f;
@@ -287,14 +321,16 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     }
   };
 
-  int it = 0;
+  int it = 0, sig_prev = -1;
   for (int t = p.T - 1; t >= 0; --t, ++it) {
     const size_t row0 = (size_t)t * B + b0;
     const uint32_t par = (uint32_t)(it & 1);
+    const float* sg = stage_s + (it & 1) * kNB * kStageRow;   // this step's saved activations
     GSCAN3_STAMP(0);
     // ---- tanh of both attentions for this step: depends only on saved activations, overlaps the X_d wait ----
     float zV[kM / 2], zT[kMaxTiB / 2];
     if (attT) {
+      const float a_qv = sg[an * kStageRow + kSgQV + ah], a_qt = sg[an * kStageRow + kSgQT + ah];
 #pragma unroll
       for (int k = 0; k < kM / 2; ++k) zV[k] = act_tanh(a_qv + KV_s[(an * kM + 2 * k + mg) * kHS + ah]);
 #pragma unroll
@@ -302,7 +338,6 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
         const int j = 2 * k + mg;
         zT[k] = (j < Ti) ? act_tanh(a_qt + KT_s[(an * Ti + j) * kHS + ah]) : 0.f;
       }
-      if (t > 0) load_att(t - 1);
     }
     GSCAN3_STAMP(1);
     if (it > 0) mbar_wait(bar0 + 8u * 4, par ^ 1u);   // dh partials of the previous iteration (X_d)
@@ -316,6 +351,9 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     GSCAN3_STAMP(2);
     // ---- B1: LSTM cell backward ------------------------------------------------------------------------
     if (cellT) {
+      const float* sc = sg + cn * kStageRow + chh;
+      const float c_gi = sc[0], c_gf = sc[kHS], c_gg = sc[2 * kHS], c_go = sc[3 * kHS], c_cprev = sc[kSgC];
+      const float c_dUh = sc[kSgDUh], c_dUcT = sc[kSgDUcT];
       float dh_t = dh_extra + c_dUh;
       if (it > 0) {
 #pragma unroll
@@ -332,13 +370,17 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
       float* dp = da_s + cn * kDaS + chh;
       dp[0] = da0; dp[kHS] = da1; dp[2 * kHS] = da2; dp[3 * kHS] = da3;
       dUcT_s[cn * kHS + chh] = c_dUcT;
-      if (cn_ok) {
-        float* dg = p.dgates + (row0 + cn) * H4 + S0 + chh;
-        dg[0] = da0; dg[kH] = da1; dg[2 * kH] = da2; dg[3 * kH] = da3;
-      }
+      c_cnew = c_cprev;   // c_{t-1} is the "new" cell state of the step about to come
     }
+    // the progress signal of the PREVIOUS step (its last stores, dq_T, were issued by the I/O threads after B11)
+    if (sig_prev >= 0 && ioT) __threadfence();
     __syncthreads();
+    if (sig_prev >= 0 && tid == 0) atomicAdd(p.progress + sig_prev, 1u);
     GSCAN3_STAMP(3);
+    // I/O warps: dgates of this step out (da_s is final and untouched until the next cell backward), the saved
+    // activations of the next step (t - 1) in: asynchronous copies into the other staging buffer, awaited two barriers later
+    io_store(da_s, kDaS, 20, p.dgates, row0, H4, true);
+    if (t > 0) io_issue(t - 1, (it + 1) & 1);   // (everybody left the other buffer at the end of the previous step)
     // ---- B2: partial dc_V (X_e) and the W_hh^T da piece of dh ----------------------------------------------
     // (the W_hh^T da piece of dh is not needed before B12: it runs later, in the shadow of the X_b exchange, so that
     //  the seven tiles of this critical product have the tensor pipe to themselves)
@@ -385,40 +427,45 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     // ---- B4: dc_V slice assembled, partial dbeta over the slice (X_a) ---------------------------------------------
     mbar_wait(bar0 + 8u * 0, par);
     if (cellT) {
-      float v = c_dUcV;
+      float v = sg[cn * kStageRow + kSgDUcV + chh];
 #pragma unroll
       for (int r = 0; r < kC; ++r) v += xcV_s[(r * kNB + cn) * kHS + chh];
       dcV_s[cn * kHS + chh] = v;
     }
     __syncthreads();
     GSCAN3_STAMP(6);
-    {
-      const int u = lane & 3;
-      constexpr int total = kNB * kM * 4;
-      for (int base = warp * 32; base < total; base += kThreads) {
-        const int item = base + lane, pair = item >> 2;
-        float s = 0.f;
-        if (item < total) {
-          const int n = pair / kM;
-          const float* kp = KV_s + pair * kHS + 5 * u;
-          const float* dp = dcV_s + n * kHS + 5 * u;
+    if (tid < kNB * kM) {
+      // one thread per (example, key) pair (288 = nine full warps): 16-byte loads of the key row and of dc_V, no
+      // shuffle reduction, and four consecutive pair sums leave as ONE 16-byte st.async per destination (lane k of a
+      // group of four -> CTA k, lane 0 also -> CTA 4): 360 instead of 1440 transactions on every receiver's mbarrier
+      // (tools/ubench_exchange.cu: 1207 -> 899 cycles for this exchange)
+      const int pair = tid, n = pair / kM;
+      const float4* kp = reinterpret_cast<const float4*>(KV_s + pair * kHS);
+      const float4* dp = reinterpret_cast<const float4*>(dcV_s + n * kHS);
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-          for (int i = 0; i < 5; ++i) s = fmaf(dp[i], kp[i], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (item < total) {
-          const uint32_t off = (uint32_t)(L.xbe + rank * kNB * kM + pair) * 4u;
-          st_async_f32(rb_u + off, s, rb_u + boff + 8u * 1);
-          if (u == 0) st_async_f32(rb_4 + off, s, rb_4 + boff + 8u * 1);
-        }
+      for (int i = 0; i < kHS / 4; ++i) {
+        const float4 k = kp[i], d = dp[i];
+        s0 = fmaf(d.x, k.x, s0); s1 = fmaf(d.y, k.y, s1); s0 = fmaf(d.z, k.z, s0); s1 = fmaf(d.w, k.w, s1);
       }
+      const float s = s0 + s1;
+      const int g0 = lane & ~3, k = lane & 3;
+      float4 v;
+      v.x = __shfl_sync(0xffffffffu, s, g0);
+      v.y = __shfl_sync(0xffffffffu, s, g0 + 1);
+      v.z = __shfl_sync(0xffffffffu, s, g0 + 2);
+      v.w = __shfl_sync(0xffffffffu, s, g0 + 3);
+      const uint32_t off = (uint32_t)(L.xbe + rank * kNB * kM + (pair & ~3)) * 4u;
+      st_async_f32x4(rb_u + off, v, rb_u + boff + 8u * 1);
+      if (k == 0) st_async_f32x4(rb_4 + off, v, rb_4 + boff + 8u * 1);
     }
     GSCAN3_STAMP(7);
     // ---- B5: softmax backward of the visual attention ---------------------------------------------------------------
     mbar_wait(bar0 + 8u * 1, par);
     if (warp < kNB) {
       const int n = warp;
+      const float s_b0 = sg[n * kStageRow + kSgBeta + lane];
+      const float s_b1 = (lane < kM - 32) ? sg[n * kStageRow + kSgBeta + 32 + lane] : 0.f;
       float d0 = s_aux0, d1 = s_aux1;
 #pragma unroll
       for (int r = 0; r < kC; ++r) d0 += xbe_s[(r * kNB + n) * kM + lane];
@@ -445,13 +492,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
         dvV_acc = fmaf(dr, z, dvV_acc);
       }
       dq += __shfl_xor_sync(0xffffffffu, dq, 1);
-      if (mg == 0) {
-        dqV_s[an * kVs + ah] = dq;
-        if (an_ok) p.dqV[(row0 + an) * kH + S0 + ah] = dq;
-      }
+      if (mg == 0) dqV_s[an * kVs + ah] = dq;
     }
     __syncthreads();
     GSCAN3_STAMP(9);
+    io_store(dqV_s, kVs, 5, p.dqV, row0, kH, false);
+    io_commit();   // the copies issued two barriers ago have landed; published by the barriers that follow
     // ---- B7: partial dq' = W_qV^T dq_V (X_b) ------------------------------------------------------------------------------
     if (warp < kTiles) {
       float o[4];
@@ -474,17 +520,16 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
 #pragma unroll
       for (int r = 0; r < kC; ++r) v += xqp_s[(r * kNB + cn) * kHS + chh];
       if (COND) {
-        const float d = v * (1.f - c_qp * c_qp);
-        dd_s[cn * kVs + chh] = d;
-        if (cn_ok) p.dd[(row0 + cn) * kH + S0 + chh] = d;
+        const float c_qp = sg[cn * kStageRow + kSgQp + chh];
+        dd_s[cn * kVs + chh] = v * (1.f - c_qp * c_qp);
       } else {
         dh_extra = v;   // q' = h_{t-1}: joins dh at the next cell backward
       }
-      if (t > 0) load_cell(t - 1, false);
     }
     GSCAN3_STAMP(11);
     if (COND) {
       __syncthreads();
+      io_store(dd_s, kVs, 5, p.dd, row0, kH, false);
       // ---- B9: the W_c[:, :H]^T dd piece of dh, and the partial dalpha completed with dd . P_cond (X_c) -------------
       if (warp >= kTiles && warp < 2 * kTiles) {
         float o[4];
@@ -551,22 +596,19 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
         }
       }
       dq += __shfl_xor_sync(0xffffffffu, dq, 1);
-      if (mg == 0) {
-        dqT_s[an * kVs + ah] = dq;
-        if (an_ok) p.dqT[(row0 + an) * kH + S0 + ah] = dq;
-      }
+      if (mg == 0) dqT_s[an * kVs + ah] = dq;
     }
-    // dq_T was the last global store of the step: publish "rows t >= t_signal are complete" (fence by every writer
-    // before the block barrier, one add per CTA after it)
-    int sig = -1;
+    __syncthreads();
+    // dq_T is the last global store of the step.  "Rows t >= t_signal are complete" is published at the first block
+    // barrier of the NEXT step (fence by the I/O threads, which issued every store, before it; one add per CTA after
+    // it), or after the loop for a signal at t = 0
+    io_store(dqT_s, kVs, 5, p.dqT, row0, kH, false);
+    sig_prev = -1;
     if (p.progress != nullptr) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (k < p.n_signals && t == p.t_signal[k]) sig = k;
+        if (k < p.n_signals && t == p.t_signal[k]) sig_prev = k;
     }
-    if (sig >= 0) __threadfence();
-    __syncthreads();
-    if (sig >= 0 && tid == 0) atomicAdd(p.progress + sig, 1u);
     GSCAN3_STAMP(14);
     // ---- B12: last piece of dh, W_qT^T dq_T, added to the earlier pieces and reduce-scattered (X_d) ------------------------------
     if (warp < kTiles) {
@@ -583,6 +625,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
   }
 
   // ---- epilogue -------------------------------------------------------------------------------------------
+  if (sig_prev >= 0) {   // a signal at the very last step (not used by the host: cut points are > 0)
+    if (ioT) __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(p.progress + sig_prev, 1u);
+  }
   mbar_wait(bar0 + 8u * 4, (uint32_t)((it - 1) & 1));
   if (cn_ok) {
     float dh = dh_extra;

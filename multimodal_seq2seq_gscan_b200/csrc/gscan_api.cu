@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "cnn.cuh"
@@ -690,22 +691,50 @@ int compute_PT(const gscan_dims& d, const float* const* P, const float* KT, floa
   return 0;
 }
 
+// stamps: [T][16 stamps][16 warps] of CTA 0.  Prints, per stamp interval, the average over the steps of the time between
+// consecutive stamps of warp 0 (the round-1 figure), and - what the chain of dependences really looks like - for every
+// stamp the average time at which the EARLIEST and the LATEST warp reached it, relative to the step's start.
+// GSCAN_TIMELINE=<file> also dumps the raw stamps.
 void print_timeline(const char* what, long long* tl, int T, cudaStream_t st) {
-  std::vector<long long> h(16 * (size_t)T);
+  constexpr int NS = v3::kTlStamps;
+  std::vector<long long> h((size_t)NS * 16 * T);
   cudaStreamSynchronize(st);
   cudaMemcpy(h.data(), tl, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost);
   cudaFree(tl);
-  double acc[16] = {0};
+  auto at = [&](int t, int k, int w) { return h[((size_t)t * NS + k) * 16 + w]; };
+  double acc[16] = {0}, lo[NS] = {0}, hi[NS] = {0};
   int n = 0;
-  for (int t = 2; t + 1 < T; ++t, ++n) {
-    for (int k = 0; k < 15; ++k) acc[k] += (double)(h[t * 16 + k + 1] - h[t * 16 + k]);
-    acc[15] += (double)(h[(t + 1) * 16] - h[t * 16 + 15]);
+  const bool rev = at(2, 0, 0) > at(T - 3, 0, 0);   // the backward sweep walks t downwards
+  for (int t = 2; t + 2 < T; ++t, ++n) {
+    const int tn = rev ? t - 1 : t + 1;
+    for (int k = 0; k < 15; ++k) acc[k] += (double)(at(t, k + 1, 0) - at(t, k, 0));
+    acc[15] += (double)(at(tn, 0, 0) - at(t, 15, 0));
+    long long t0 = at(t, 0, 0);
+    for (int w = 1; w < 16; ++w) if (at(t, 0, w) && at(t, 0, w) < t0) t0 = at(t, 0, w);
+    for (int k = 0; k < NS; ++k) {
+      long long mn = 0, mx = 0;
+      for (int w = 0; w < 16; ++w) {
+        const long long v = at(t, k, w);
+        if (!v) continue;
+        if (!mn || v < mn) mn = v;
+        if (v > mx) mx = v;
+      }
+      if (mx) { lo[k] += (double)(mn - t0); hi[k] += (double)(mx - t0); }
+    }
   }
   if (n == 0) return;
   fprintf(stderr, "[gscan] %s timeline (avg cycles per phase over %d steps):", what, n);
   double tot = 0;
   for (int k = 0; k < 16; ++k) { fprintf(stderr, " %d:%.0f", k, acc[k] / n); tot += acc[k] / n; }
   fprintf(stderr, " total %.0f\n", tot);
+  fprintf(stderr, "[gscan] %s stamps reached at (first warp / last warp, cycles after the step's first stamp):", what);
+  for (int k = 0; k < NS; ++k) fprintf(stderr, " %d:%.0f/%.0f", k, lo[k] / n, hi[k] / n);
+  fprintf(stderr, "\n");
+  const char* path = getenv("GSCAN_TIMELINE");
+  if (path && path[0] && strcmp(path, "1") != 0) {
+    std::string f = std::string(path) + (rev ? ".bwd.bin" : ".fwd.bin");
+    if (FILE* fp = fopen(f.c_str(), "wb")) { fwrite(h.data(), sizeof(long long), h.size(), fp); fclose(fp); }
+  }
 }
 
 int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, const Layout& L, v3::DecFwd3P p,
@@ -724,7 +753,8 @@ int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, con
   long long* tl = nullptr;
   if (want_timeline && !greedy && cond) {   // the instrumented instantiation exists for the paper configuration only
     TRY((v3_fwd_prepare<true, false, true>(bytes)));
-    cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
+    cudaMalloc(&tl, sizeof(long long) * v3::kTlStamps * 16 * p.T);
+    cudaMemsetAsync(tl, 0, sizeof(long long) * v3::kTlStamps * 16 * p.T, st);
     p.timeline = tl;
   }
   const int grid = ceil_div(d.B, v3::kNB) * v3::kC;
@@ -797,7 +827,8 @@ int launch_dec_bwd_v3(const gscan_dims& d, v3::DecBwd3P p, cudaStream_t st) {
   long long* tl = nullptr;
   if (want_timeline && cond) {
     TRY((v3_bwd_prepare<true, true>(bytes)));
-    cudaMalloc(&tl, sizeof(long long) * 16 * p.T);
+    cudaMalloc(&tl, sizeof(long long) * v3::kTlStamps * 16 * p.T);
+    cudaMemsetAsync(tl, 0, sizeof(long long) * v3::kTlStamps * 16 * p.T, st);
     p.timeline = tl;
   }
   const int grid = ceil_div(d.B, v3::kNB) * v3::kC;
