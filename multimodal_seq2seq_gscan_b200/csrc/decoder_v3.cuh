@@ -26,6 +26,11 @@ constexpr int kXS = 104;   // row stride of the gathered activation vectors (13 
 constexpr int kKSteps = 13;
 constexpr int kGS = 84;    // row stride of the gate pre-activation scratch (bank spread)
 constexpr int kMaxTi = 16;
+constexpr int kXeBuf = kNB * kG4 + 4;   // one Xe staging buffer: [8][80] + four zero words (the "no Xe term" slot)
+constexpr int kOutRow = 120;    // [gates i f g o: 80 | h_t: 20 | c_t: 20] per example, staged by the cell threads
+constexpr int kIoWarp0 = 14, kIoThreads = 64;   // backward sweep: warps 14, 15 move the per-step global traffic
+constexpr int kIoWarp0F = 8, kIoThreadsF = 256; // forward sweep: warps 8-15 (stage D / C owners and the spare warp, idle
+                                                // outside their own stage) - one or two 16-byte accesses per thread and site
 constexpr int kTlStamps = 24;   // phase stamps per step of the instrumented (TL) instantiations: 0-15 phases, 16+ sub-phases
 
 // ---- PTX helpers ------------------------------------------------------------------------------
@@ -125,6 +130,7 @@ __device__ __forceinline__ void mv_tile(const uint32_t (&whi)[kKSteps][4], const
 struct FwdSmem {
   int hfull, qpfull, cvfull, xT, xV, P, KT, KV, qT, ch, qV, g, al, be, vT, vV, bc, len, bars, wlo, total;
   int xeTab, outE, wo, u, xL, tok;   // greedy decoding only
+  int xe, cT, out;                   // training only: staging of Xe (double buffered), c_T, [gates | h | c] (see I/O warps)
 };
 __host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond, int greedy_V = 0) {
   FwdSmem s{};
@@ -159,6 +165,10 @@ __host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond, int greedy_V = 0) 
     s.u = take(kNB * 3 * kHS);     // [h | c_T | c_V] slices of the current step
     s.xL = take(kC * kNB * Vp);    // partial logits from every rank
     s.tok = take(3 * kNB + 4);     // tok, alive, flag (ints)
+  } else {
+    s.xe = take(2 * kXeBuf);       // Xe rows of this and of the next step (filled by cp.async one step ahead) + zero pad
+    s.cT = take(kNB * kHS);        // c_T slice of this step
+    s.out = take(kNB * kOutRow);   // activated gates, h_t, c_t of this step
   }
   s.total = o;
   return s;
@@ -460,11 +470,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
 
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar0 = smem_base + (uint32_t)L.bars * 4u;   // [0] xT  [1] qp  [2] xV  [3] cv  [4] h  [5] logits
-  uint32_t rb[kC];
-#pragma unroll
-  for (int d = 0; d < kC; ++d) rb[d] = mapa_u32(smem_base, (uint32_t)d);
-  const uint32_t rb_u = mapa_u32(smem_base, (uint32_t)(lane & 3)), rb_4 = rb[4];
-  const uint32_t rb_8 = mapa_u32(smem_base, (uint32_t)min(lane & 7, kC - 1));
+  // shared-memory windows of the peer CTAs: one `mapa` where they are used (cheaper than seven registers held for the
+  // whole sweep: the kernel sits at the 128-register limit)
+#define RB(d) mapa_u32(smem_base, (uint32_t)(d))
+#define RB_U RB(lane & 3)
+#define RB_4 RB(4)
+#define RB_8 RB(min(lane & 7, kC - 1))
   const uint32_t boff = (uint32_t)L.bars * 4u;
 
   // ---- resident weight fragments; the content depends on the warp's role ---------------------------------
@@ -584,19 +595,71 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   }
   int my_len = 0, my_steps = 0;   // greedy bookkeeping of lane n < kNB of warp 15
   float bs0 = 0.f, bs1 = 0.f;   // sum over steps of beta[warp][lane], beta[warp][lane + 32]
-  // Xe prefetch for the gate outputs this lane owns after its stage-A tile: rows lr0, lr0+8 x examples nF, nF+1
-  const bool gate0 = roleA && lr0 >= 2 * kHS && lr0 < 6 * kHS, gate1 = roleA && lr0 + 8 >= 2 * kHS && lr0 + 8 < 6 * kHS;
-  const int xe_col0 = gate0 ? ((lr0 - 2 * kHS) / kHS) * kH + S0 + (lr0 % kHS) : 0;
-  const int xe_col1 = gate1 ? ((lr0 + 8 - 2 * kHS) / kHS) * kH + S0 + ((lr0 + 8) % kHS) : 0;
-  float xe[4] = {0.f, 0.f, 0.f, 0.f};
-  auto load_xe = [&](size_t rowbase) {
-#pragma unroll
-    for (int m = 0; m < 2; ++m) {
-      if (gate0 && nF + m < nb) xe[m] = __ldg(p.Xe + (rowbase + nF + m) * H4 + xe_col0);
-      if (gate1 && nF + m < nb) xe[2 + m] = __ldg(p.Xe + (rowbase + nF + m) * H4 + xe_col1);
+  // Round 2 (training sweep): everything a step reads from or writes to global memory goes through shared memory
+  // and the two I/O warps (14, 15: stage C apart, idle) in 16-byte coalesced accesses.  Round 1 had every thread of the
+  // stage-A epilogue, the softmaxes, the c_T / c_V combinations and the LSTM cell store its own 4-byte words (saved
+  // activations for the backward pass) and prefetch its own 4 words of Xe: taking those accesses out of the kernel
+  // shortened it from 0.88 to 0.75 ms (experiment) - address arithmetic and LSU slots on the critical
+  // path of issue- and latency-bound phases.
+  float* xe_s = smem + L.xe;
+  float* cT_s = smem + L.cT;
+  float* out_s = smem + L.out;
+  const bool ioT = !GREEDY && warp >= kIoWarp0F;
+  const int io = tid - kIoWarp0F * 32;
+  // I/O threads [first, first + kNB * nq): one float4 each, shared src_s[n * sstride + 4q] -> global
+  // dst[(grow0 + n) * gstride + S0 + col(q)], col(q) = 4q, or for the gate block (q / 5) * H + 4 (q % 5)
+  auto io_rows = [&](int first, const float* src_s, int sstride, int nq, float* dst, size_t grow0, int gstride,
+                     bool gate_cols) {
+    const int f = io - first;
+    if (!ioT || f < 0 || f >= kNB * nq) return;
+    const int n = f / nq, q = f - n * nq;
+    if (n < nb) {
+      const int gcol = gate_cols ? (q / 5) * kH + 4 * (q % 5) : 4 * q;
+      *reinterpret_cast<float4*>(dst + (grow0 + n) * gstride + S0 + gcol) = lds4(src_s + n * sstride + 4 * q);
     }
   };
-  if (!GREEDY) load_xe((size_t)b0);
+  // Xe rows of step `t` -> staging buffer `buf` by the I/O threads [first, first + 160): 16-byte asynchronous copies,
+  // awaited by xe_wait() before a later barrier
+  auto xe_issue = [&](int first, int t, int buf) {
+    const int f = io - first;
+    if (!ioT) return;
+    if (f >= 0 && f < kNB * (kG4 / 4)) {
+      const int n = f / (kG4 / 4), q = f - n * (kG4 / 4);
+      if (n < nb) {
+        const uint32_t dst = smem_u32(xe_s + buf * kXeBuf + n * kG4 + 4 * q);
+        const float* src = p.Xe + ((size_t)t * B + b0 + n) * H4 + (q / 5) * kH + S0 + 4 * (q % 5);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto xe_wait = [&]() {
+    if (ioT) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  };
+  // Stage-A epilogue of the training sweep: where each of the four tile results of this lane goes (float offset in
+  // shared memory, low half) and which staged Xe word is added to it (offset in a staging buffer, high half; the zero
+  // pad for rows that are not LSTM gates).  Decoded once: the epilogue is 4 x (LDS, FADD, STS) without branches
+  // (round 1: row-type decode, divergent branches and 64-bit global addresses per result, ~800 cycles per step).
+  uint32_t eo[4] = {0u, 0u, 0u, 0u};
+  if (!GREEDY && roleA) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int lr = lr0 + 8 * (j >> 1), n = nF + (j & 1);
+      const int type = lr / kHS, i = lr - type * kHS;
+      int dst, x = kNB * kG4;   // zero pad
+      if (type == 0) dst = L.qT + n * kHS + i;
+      else if (type == 1) dst = (COND ? L.ch : L.qV) + n * kHS + i;
+      else if (type < 6) { dst = L.g + n * kGS + lr - 2 * kHS; x = n * kG4 + lr - 2 * kHS; }
+      else dst = L.g + n * kGS + kG4;   // rows 120..127 of the last tile: a pad column of the gate scratch
+      eo[j] = (uint32_t)dst | ((uint32_t)x << 16);
+    }
+  }
+  if (!GREEDY) {
+    for (int i = tid; i < 2 * kXeBuf; i += kThreads) xe_s[i] = 0.f;   // rows of absent examples and the pads stay zero
+    __syncthreads();
+    xe_issue(0, 0, 0);
+    xe_wait();
+  }
   // all CTAs of the cluster must have initialised their barriers and buffers before any remote store
   __syncthreads();
   cluster_barrier();
@@ -676,35 +739,35 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     if (roleA) {
+      if (GREEDY) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int lr = lr0 + 8 * (j >> 1), n = nF + (j & 1);
-        const int type = lr / kHS, i = lr - type * kHS;
-        if (type == 0) {
-          qT_s[n * kHS + i] = o[j];
-          if (!GREEDY && n < nb) p.qT[(row0 + n) * kH + S0 + i] = o[j];
-        } else if (type == 1) {
-          if (COND) {
-            ch_s[n * kHS + i] = o[j];
-          } else {
-            qV_s[n * kHS + i] = o[j];
-            if (!GREEDY && n < nb) {
-              p.qV[(row0 + n) * kH + S0 + i] = o[j];
-              p.Qp[(row0 + n) * kH + S0 + i] = hfull_s[n * kXS + S0 + i];
-            }
-          }
-        } else if (type < 6) {
-          g_s[n * kGS + lr - 2 * kHS] = o[j] + (GREEDY ? xeTab_s[tok_s[n] * kG4 + lr - 2 * kHS] : xe[j]);
+        for (int j = 0; j < 4; ++j) {
+          const int lr = lr0 + 8 * (j >> 1), n = nF + (j & 1);
+          const int type = lr / kHS, i = lr - type * kHS;
+          if (type == 0) qT_s[n * kHS + i] = o[j];
+          else if (type == 1) (COND ? ch_s : qV_s)[n * kHS + i] = o[j];
+          else if (type < 6) g_s[n * kGS + lr - 2 * kHS] = o[j] + xeTab_s[tok_s[n] * kG4 + lr - 2 * kHS];
         }
+      } else {
+        const float* xb = xe_s + (t & 1) * kXeBuf;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) smem[eo[j] & 0xffffu] = o[j] + xb[eo[j] >> 16];
       }
       GSCAN3_STAMP(17);
-      if (!GREEDY && t + 1 < p.T) load_xe(row0 + B);
     }
     GSCAN3_STAMP(18);
     __syncthreads();
     GSCAN3_STAMP(2);
+    if (!GREEDY) {
+      // I/O warps: q_T of this step (and q_V, q' = h_{t-1} without conditional attention)
+      io_rows(0, qT_s, kHS, 5, p.qT, row0, kH, false);
+      if (!COND) {
+        io_rows(40, qV_s, kHS, 5, p.qV, row0, kH, false);
+        io_rows(80, hfull_s + S0, kXS, 5, p.Qp, row0, kH, false);
+      }
+    }
     // ---- textual attention: partial scores over the local slice, summed over ranks (X1) ---------------
-    partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, rb_8, rb_4, boff + 0u);
+    partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, RB_8, RB_4, boff + 0u);
     GSCAN3_STAMP(3);
     mbar_wait(bar0 + 8u * 0, par);
     GSCAN3_STAMP(4);
@@ -723,7 +786,6 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       const float a = e * (1.0f / sum);
       if (lane < Ti) {
         al_s[n * Ti + lane] = a;
-        if (!GREEDY && n < nb && rank == n % kC) p.alpha[(row0 + n) * Ti + lane] = a;
         if (GREEDY && p.g_alphas && n < nb && rank == n % kC && alive_s[n])
           p.g_alphas[((size_t)(b0 + n) * p.T + t) * Ti + lane] = a;
       }
@@ -731,6 +793,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(19);
     __syncthreads();
     GSCAN3_STAMP(5);
+    if (ioT) {   // alpha rows of the examples this rank writes (Ti floats each: no 16-byte granularity in general)
+      for (int f = io; f < kNB * Ti; f += kIoThreadsF) {
+        const int n = f / Ti;
+        if (n < nb && rank == n % kC) p.alpha[(row0 + n) * Ti + (f - n * Ti)] = al_s[f];
+      }
+    }
     // ---- everything linear in c_T through P_j = W K^T_j: q' slice (X3), gate contributions, c_T slice ----
     if (tid < kNB * (QB + 5)) {
       const int n = tid / (QB + 5), q = tid - n * (QB + 5);
@@ -752,8 +820,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         qq.w = act_tanh(chv.w + o.w + bcv.w);
         const uint32_t off = (uint32_t)(L.qpfull + n * kXS + S0 + 4 * q) * 4u;
 #pragma unroll
-        for (int d = 0; d < kC; ++d) st_async_f32x4(rb[d] + off, qq, rb[d] + boff + 8u * 1);
-        if (!GREEDY && n < nb) *reinterpret_cast<float4*>(p.Qp + (row0 + n) * kH + S0 + 4 * q) = qq;
+        for (int d = 0; d < kC; ++d) {
+          const uint32_t w = RB(d);
+          st_async_f32x4(w + off, qq, w + boff + 8u * 1);
+        }
       } else if (q < QB) {
         float4* gp = reinterpret_cast<float4*>(g_s + n * kGS + 4 * q - (COND ? kHS : 0));
         float4 gv = *gp;
@@ -761,8 +831,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         *gp = gv;
       } else if (GREEDY) {
         *reinterpret_cast<float4*>(u_s + n * 3 * kHS + kHS + 4 * (q - QB)) = o;
-      } else if (n < nb) {
-        *reinterpret_cast<float4*>(p.U + (row0 + B + n) * H4 + 2 * kH + S0 + 4 * (q - QB)) = o;
+      } else {
+        *reinterpret_cast<float4*>(cT_s + n * kHS + 4 * (q - QB)) = o;
       }
     }
     GSCAN3_STAMP(6);
@@ -776,17 +846,25 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = lr0 + 8 * (j >> 1), n = nF + (j & 1);
-          if (r < kHS) {
-            qV_s[n * kHS + r] = o[j];
-            if (!GREEDY && n < nb) p.qV[(row0 + n) * kH + S0 + r] = o[j];
-          }
+          if (r < kHS) qV_s[n * kHS + r] = o[j];
         }
       }
     }
     __syncthreads();
     GSCAN3_STAMP(8);
+    if (!GREEDY) {
+      // I/O warps: c_T (row group t + 1 of U), and with conditional attention q_V and q' (this CTA's slice of q' came
+      // back through its own X3 store)
+      io_rows(0, cT_s, kHS, 5, p.U + 2 * kH, row0 + B, H4, false);
+      if (COND) {
+        io_rows(40, qV_s, kHS, 5, p.qV, row0, kH, false);
+        io_rows(80, qpfull_s + S0, kXS, 5, p.Qp, row0, kH, false);
+      }
+      // the Xe rows of the next step into the other staging buffer (last read by the stage-A epilogue of step t - 1)
+      if (t + 1 < p.T) xe_issue(96, t + 1, (t + 1) & 1);
+    }
     // ---- visual attention: partial scores (X4), softmax, c_V slice gathered (X5) -------------------------
-    partial_scores_vec<kM, 1>(qV_s, KV_s, vV_s, kM, L.xV, rank, rb_u, rb_4, boff + 8u * 2);
+    partial_scores_vec<kM, 1>(qV_s, KV_s, vV_s, kM, L.xV, rank, RB_U, RB_4, boff + 8u * 2);
     GSCAN3_STAMP(9);
     mbar_wait(bar0 + 8u * 2, par);
     GSCAN3_STAMP(10);
@@ -811,10 +889,6 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         be_s[n * kM + 32 + lane] = w1;
         if (counted) bs1 += w1;
       }
-      if (!GREEDY && n < nb && rank == n % kC) {
-        p.beta[(row0 + n) * kM + lane] = w0;
-        if (lane < kM - 32) p.beta[(row0 + n) * kM + 32 + lane] = w1;
-      }
       if (GREEDY && p.g_betas && n < nb && rank == n % kC && counted) {
         float* gb = p.g_betas + ((size_t)(b0 + n) * p.T + t) * kM;
         gb[lane] = w0;
@@ -824,6 +898,13 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(20);
     __syncthreads();
     GSCAN3_STAMP(21);
+    if (ioT) {   // beta rows (36 floats = 9 x 16 bytes) of the examples this rank writes
+      if (io < kNB * (kM / 4)) {
+        const int n = io / (kM / 4), q = io - n * (kM / 4);
+        if (n < nb && rank == n % kC)
+          *reinterpret_cast<float4*>(p.beta + (row0 + n) * kM + 4 * q) = lds4(be_s + n * kM + 4 * q);
+      }
+    }
     if (tid < kNB * 5 * 4) {
       // 4 lanes per (example, hidden quad): each sums 9 of the 36 cells, then a butterfly all-reduce
       const int k = tid >> 2, u = tid & 3;
@@ -845,13 +926,13 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         o.w += __shfl_xor_sync(0xffffffffu, o.w, sh);
       }
       const uint32_t off = (uint32_t)(L.cvfull + n * kXS + S0 + 4 * hq) * 4u;
-      st_async_f32x4(rb_u + off, o, rb_u + boff + 8u * 3);
-      if (u == 0) st_async_f32x4(rb_4 + off, o, rb_4 + boff + 8u * 3);
-      if (GREEDY) {
-        if (u == 1) *reinterpret_cast<float4*>(u_s + n * 3 * kHS + 2 * kHS + 4 * hq) = o;
-      } else if (u == 1 && n < nb) {
-        *reinterpret_cast<float4*>(p.U + (row0 + B + n) * H4 + 3 * kH + S0 + 4 * hq) = o;
+      const uint32_t wu = RB_U;
+      st_async_f32x4(wu + off, o, wu + boff + 8u * 3);
+      if (u == 0) {
+        const uint32_t w4 = RB_4;
+        st_async_f32x4(w4 + off, o, w4 + boff + 8u * 3);
       }
+      if (GREEDY && u == 1) *reinterpret_cast<float4*>(u_s + n * 3 * kHS + 2 * kHS + 4 * hq) = o;
     }
     GSCAN3_STAMP(11);
     mbar_wait(bar0 + 8u * 3, par);
@@ -866,6 +947,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(22);
     __syncthreads();
     GSCAN3_STAMP(13);
+    // I/O warps: c_V (this CTA's slice came back through its own X5 store), row group t + 1 of U
+    if (!GREEDY) {
+      io_rows(0, cvfull_s + S0, kXS, 5, p.U + 3 * kH, row0 + B, H4, false);
+      xe_wait();   // issued after stage C; published by the barriers before the next stage-A epilogue
+    }
     if (tid < kNB * kHS) {
       const float* gp = g_s + cn * kGS + chh;
       const float ig = act_sigmoid(gp[0]), fg = act_sigmoid(gp[kHS]), gg = act_tanh(gp[2 * kHS]), og = act_sigmoid(gp[3 * kHS]);
@@ -881,17 +967,27 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         v.z = __shfl_sync(0xffffffffu, hn, g0 + 2);
         v.w = __shfl_sync(0xffffffffu, hn, g0 + 3);
         const uint32_t off = (uint32_t)(L.hfull + cn * kXS + S0 + (chh & ~3)) * 4u;
-        st_async_f32x4(rb_u + off, v, rb_u + boff + 8u * 4);
-        if (k == 0) st_async_f32x4(rb_4 + off, v, rb_4 + boff + 8u * 4);
+        const uint32_t wu = RB_U;
+        st_async_f32x4(wu + off, v, wu + boff + 8u * 4);
+        if (k == 0) {
+          const uint32_t w4 = RB_4;
+          st_async_f32x4(w4 + off, v, w4 + boff + 8u * 4);
+        }
       }
       if (GREEDY) u_s[cn * 3 * kHS + chh] = hn;
-      if (!GREEDY && cn < nb) {
-        const size_t row = row0 + cn;
-        float* go = p.gates + row * H4 + S0 + chh;
-        go[0] = ig; go[kH] = fg; go[2 * kH] = gg; go[3 * kH] = og;
-        p.U[(row + B) * H4 + kH + S0 + chh] = hn;
-        p.Cs[(row + B) * kH + S0 + chh] = c_reg;
+      if (!GREEDY) {   // staged; written out by the I/O warps after the first barrier of the next step (or after the loop)
+        float* op = out_s + cn * kOutRow + chh;
+        op[0] = ig; op[kHS] = fg; op[2 * kHS] = gg; op[3 * kHS] = og; op[4 * kHS] = hn; op[5 * kHS] = c_reg;
+        asm volatile("bar.arrive 1, %0;" ::"n"(kNB * kHS + kIoThreadsF) : "memory");   // hand-off to the I/O warps
       }
+    }
+    if (ioT) {
+      // the I/O warps take the staged cell outputs as soon as the 160 cell threads have written them (named barrier 1:
+      // nobody else waits) and write them out in the shadow of the next step's stage A
+      asm volatile("bar.sync 1, %0;" ::"n"(kNB * kHS + kIoThreadsF) : "memory");
+      io_rows(0, out_s, kOutRow, 20, p.gates, row0, H4, true);
+      io_rows(160, out_s + 4 * kHS, kOutRow, 5, p.U + kH, row0 + B, H4, false);   // h_t: row group t + 1 of U
+      io_rows(200, out_s + 5 * kHS, kOutRow, 5, p.Cs, row0 + B, kH, false);      // c_t: row group t + 1 of Cs
     }
     GSCAN3_STAMP(14);
     if (GREEDY) {
@@ -913,8 +1009,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         if (item < total) {
           const uint32_t off = (uint32_t)(L.xL + rank * kNB * V + pair) * 4u;
-          st_async_f32(rb_u + off, s, rb_u + boff + 8u * 5);
-          if (u == 0) st_async_f32(rb_4 + off, s, rb_4 + boff + 8u * 5);
+          const uint32_t wu = RB_U;
+          st_async_f32(wu + off, s, wu + boff + 8u * 5);
+          if (u == 0) {
+            const uint32_t w4 = RB_4;
+            st_async_f32(w4 + off, s, w4 + boff + 8u * 5);
+          }
         }
       }
     }
@@ -937,6 +1037,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   // no CTA may exit while stores from its peers can still be in flight towards it
   cluster_barrier();
 }
+
+#undef RB
+#undef RB_U
+#undef RB_4
+#undef RB_8
 
 }  // namespace v3
 }  // namespace gscan

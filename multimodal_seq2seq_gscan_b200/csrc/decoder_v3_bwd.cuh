@@ -29,7 +29,7 @@ constexpr int kMaxTiB = 16;   // text positions per attention thread: 8 register
 //   [gates i f g o: 80 | c_{t-1}: 20 | dU_h: 20 | dU_cT: 20 | dU_cV: 20 | q': 20 | q_V: 20 | q_T: 20 | beta: 36]
 constexpr int kStageRow = 256, kStageQ = kStageRow / 4;
 constexpr int kSgC = 80, kSgDUh = 100, kSgDUcT = 120, kSgDUcV = 140, kSgQp = 160, kSgQV = 180, kSgQT = 200, kSgBeta = 220;
-constexpr int kIoWarp0 = 14, kIoThreads = 64;
+
 
 struct BwdSmem {
   int W, KV, KT, P, da, dqV, dd, dqT, dUcT, dhpart, dcV, xcV, xbe, xqp, xal, xdh, drV, drT, a1, vT, vV, len, bars, stage, total;
