@@ -22,8 +22,10 @@ namespace gscan {
 namespace v3 {
 
 constexpr int kH = 100, kC = 5, kHS = 20, kM = 36, kG4 = 80, kNB = 8, kThreads = 512;
-constexpr int kXS = 104;   // row stride of the gathered activation vectors (13 k-steps of 8; pad stays zero)
-constexpr int kKSteps = 13;
+constexpr int kXS = 112;   // row stride of the gathered activation vectors (7 k-steps of 16; pad stays zero; 112 = 16 mod 32
+                           // words: the 16-byte B-operand loads of two rows x four lanes touch every bank once)
+constexpr int kKSteps = 13;   // k-steps of 8 of the tf32 tile (mv_tile: micro-benchmarks, backward sweep helpers)
+constexpr int kK16 = 7;       // k-steps of 16 of the f16 tile (mv_tile16: the forward sweep)
 constexpr int kGS = 84;    // row stride of the gate pre-activation scratch (bank spread)
 constexpr int kMaxTi = 16;
 constexpr int kXeBuf = kNB * kG4 + 4;   // one Xe staging buffer: [8][80] + four zero words (the "no Xe term" slot)
@@ -126,6 +128,52 @@ __device__ __forceinline__ void mv_tile(const uint32_t (&whi)[kKSteps][4], const
   for (int j = 0; j < 4; ++j) o[j] = d0[j] + (d1[j] + d2[j]);
 }
 
+// ---- split-precision mat-vec on f16 operands (round 2, forward sweep) ----------------------------------------------
+// Every mma.sync shape issues at 8.0 cycles per instruction per scheduler on B200, whatever it computes
+// (tools/ubench_hmma_rates.cu: tf32 m16n8k8 = 1024 MAC, f16 m16n8k16 = 2048 MAC, same rate), and the three mat-vec
+// stages of a step are bound by exactly that (tools/ubench_mvtile.cu).  An fp32 value splits into two f16 operands the
+// same way it splits into two tf32 ones - 11 significant bits each: hi = f16(x), lo' = f16((x - hi) * 2^11), the
+// scaling keeps lo' in f16's normal range - so the product costs 3 x 7 instructions of K = 16 instead of 3 x 13 of K = 8:
+//     W x  ~=  W_hi x_hi + 2^-11 (W_lo' x_hi + W_hi x_lo')          (dropped: W_lo x_lo ~ 2^-22 relative, as before)
+// Forward only: weights and activations (h, q' in (-1, 1); c_V a convex combination of keys) are far inside f16's
+// range, and values below f16's normal range keep their precision through lo' (|x - hi| <= 2^-25 absolute).  The
+// backward sweep multiplies gradients of arbitrary magnitude and stays on tf32.
+__device__ __forceinline__ void mma_f16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+constexpr float kLoScale = 2048.f, kLoInv = 1.f / 2048.f;
+// (x0, x1) -> packed f16 pair of the rounded values (x0 in the low half) and of the scaled remainders
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  float h0, h1;
+  asm("{\n.reg .f16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(h0), "=f"(h1) : "r"(hi));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"((x1 - h1) * kLoScale), "f"((x0 - h0) * kLoScale));
+}
+// One 16-row tile: o = W[16 x 112] . x[8 examples][112]^T.  Lane (g = lane>>2, t = lane&3) supplies for k-step s the
+// operand slots (k = 2t, 2t+1 | 2t+8, 2t+9) from the physical columns (16s + 4t, +1 | +2, +3), for A and B alike, so
+// that B comes from ONE 16-byte load.  Result layout as mv_tile: o[0], o[1] = row g, examples 2t, 2t+1; o[2], o[3] = row g + 8.
+__device__ __forceinline__ void mv_tile16(const uint32_t (&whi)[kK16][4], const uint4* __restrict__ wlo_lane,
+                                          const float* __restrict__ x_lane, float (&o)[4]) {
+  float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < kK16; ++s) {
+    const float4 xv = lds4(x_lane + 16 * s);
+    const uint4 lo = wlo_lane[s * 32];
+    uint32_t bh0, bl0, bh1, bl1;
+    split_f16x2(xv.x, xv.y, bh0, bl0);
+    split_f16x2(xv.z, xv.w, bh1, bl1);
+    mma_f16(d0, whi[s][0], whi[s][1], whi[s][2], whi[s][3], bh0, bh1);
+    mma_f16(d1, lo.x, lo.y, lo.z, lo.w, bh0, bh1);
+    mma_f16(d2, whi[s][0], whi[s][1], whi[s][2], whi[s][3], bl0, bl1);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) o[j] = fmaf(kLoInv, d1[j] + d2[j], d0[j]);
+}
+
 // ---- shared-memory layout (float offsets) --------------------------------------------------------
 struct FwdSmem {
   int hfull, qpfull, cvfull, xT, xV, P, KT, KV, qT, ch, qV, g, al, be, vT, vV, bc, len, bars, wlo, total;
@@ -156,7 +204,7 @@ __host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond, int greedy_V = 0) 
   s.bc = take(kHS);
   s.len = take(kNB);
   s.bars = take(16);   // 5 mbarriers (8 bytes each)
-  s.wlo = take(15 * kKSteps * 32 * 4);   // W_lo fragments: [role warp][k-step][lane] float4
+  s.wlo = take(15 * kK16 * 32 * 4);   // W_lo' fragments: [role warp][k-step][lane] four packed f16 pairs
   if (greedy_V > 0) {
     const int V = greedy_V, Vp = (V + 3) & ~3;
     s.xeTab = take(V * kG4);       // this CTA's columns of Emb . W_ih[:, :H]^T + b_ih + b_hh
@@ -484,8 +532,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   //   warps 13-14 stage C  tile w-13 of W_qV (20 rows, conditional attention only)    (input q')
   const int fg = lane >> 2, ft = lane & 3;   // fragment coordinates
   const bool roleA = warp < 8, roleD = warp >= 8 && warp < 13, roleC = COND && (warp == 13 || warp == 14);
-  uint32_t whi[kKSteps][4];
-  float4* wlo_lane = reinterpret_cast<float4*>(smem + L.wlo) + (size_t)min(warp, 14) * kKSteps * 32 + lane;
+  uint32_t whi[kK16][4];
+  uint4* wlo_lane = reinterpret_cast<uint4*>(smem + L.wlo) + (size_t)min(warp, 14) * kK16 * 32 + lane;
   int lr0 = 0;   // local output row of o[0], o[1]; o[2], o[3] belong to row lr0 + 8
   {
     const float *r0 = nullptr, *r1 = nullptr;
@@ -515,15 +563,17 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       r1 = rowC(lr0 + 8);
     }
 #pragma unroll
-    for (int s = 0; s < kKSteps; ++s) {
-      const int k = 8 * s + 2 * ft;
-      float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
-      if (r0 && k < kH) a = __ldg(reinterpret_cast<const float2*>(r0 + k));
-      if (r1 && k < kH) b = __ldg(reinterpret_cast<const float2*>(r1 + k));
-      whi[s][0] = tf32_hi(a.x); whi[s][1] = tf32_hi(b.x); whi[s][2] = tf32_hi(a.y); whi[s][3] = tf32_hi(b.y);
-      if (warp < 15)
-        wlo_lane[s * 32] = make_float4(__uint_as_float(tf32_lo(a.x)), __uint_as_float(tf32_lo(b.x)),
-                                       __uint_as_float(tf32_lo(a.y)), __uint_as_float(tf32_lo(b.y)));
+    for (int s = 0; s < kK16; ++s) {
+      const int k = 16 * s + 4 * ft;   // four consecutive weights of rows lr0 and lr0 + 8 (rows are 16-byte aligned)
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 && k < kH) a = ldg4(r0 + k);
+      if (r1 && k < kH) b = ldg4(r1 + k);
+      uint32_t la, lb, lc, ld;
+      split_f16x2(a.x, a.y, whi[s][0], la);
+      split_f16x2(b.x, b.y, whi[s][1], lb);
+      split_f16x2(a.z, a.w, whi[s][2], lc);
+      split_f16x2(b.z, b.w, whi[s][3], ld);
+      if (warp < 15) wlo_lane[s * 32] = make_uint4(la, lb, lc, ld);
     }
   }
   const int nF = 2 * ft;   // examples nF, nF + 1 are owned after a tile product
@@ -726,7 +776,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(1);
     // ---- stage A: everything that depends only on h_{t-1} ---------------------------------------------
     float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (roleA) mv_tile(whi, wlo_lane, hfull_s + fg * kXS + 2 * ft, o);
+    if (roleA) mv_tile16(whi, wlo_lane, hfull_s + fg * kXS + 4 * ft, o);
     GSCAN3_STAMP(16);
     if (GREEDY) {
       // The token of the previous step is picked HERE, by the otherwise idle warp 15, while the role-A warps run the
@@ -842,7 +892,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       GSCAN3_STAMP(7);
       if (roleC) {
         float o[4];
-        mv_tile(whi, wlo_lane, qpfull_s + fg * kXS + 2 * ft, o);
+        mv_tile16(whi, wlo_lane, qpfull_s + fg * kXS + 4 * ft, o);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = lr0 + 8 * (j >> 1), n = nF + (j & 1);
@@ -940,7 +990,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     // ---- stage D: c_V contribution to the gates, then the LSTM cell ---------------------------------------
     if (roleD) {
       float o[4];
-      mv_tile(whi, wlo_lane, cvfull_s + fg * kXS + 2 * ft, o);
+      mv_tile16(whi, wlo_lane, cvfull_s + fg * kXS + 4 * ft, o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) g_s[(nF + (j & 1)) * kGS + lr0 + 8 * (j >> 1)] += o[j];
     }
