@@ -223,8 +223,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
   const int fg = lane >> 2, ft = lane & 3, nF = 2 * ft;   // mma fragment coordinates
   const bool cellT = tid < kNB * kHS;                     // (example cn, hidden S0 + chh)
   const int cn = tid / kHS, chh = tid - cn * kHS;
-  const bool attT = tid < 2 * kNB * kHS;                  // (example an, hidden S0 + ah), keys 2k + mg
-  const int an = attT ? (tid >> 1) / kHS : 0, ah = attT ? (tid >> 1) % kHS : 0, mg = tid & 1;
+  // 320 attention threads (example an, hidden S0 + ah), keys 2k + mg: warps 0-6 and 13-15.  Their 26 tanh per step
+  // are recomputed at the top of a step, right after the critical warps 7-13 have sent the last piece of dh (B12): only
+  // warp 13 has both jobs (round 1 / first half of round 2: warps 0-9, three warps double-booked, ~450 cycles per step)
+  const bool attT = warp < kTiles || warp >= 13;
+  const int aidx = warp < kTiles ? tid : tid - (13 - kTiles) * 32;
+  const int an = attT ? (aidx >> 1) / kHS : 0, ah = attT ? (aidx >> 1) % kHS : 0, mg = tid & 1;
   const bool an_ok = attT && an < nb;
   const bool cn_ok = cellT && cn < nb;
 
@@ -307,6 +311,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
                  bytes_al = (uint32_t)(kC * kNB * Ti * 4);
   const float4* w_tile = W_s + (size_t)(warp < kTiles ? warp : (warp < 2 * kTiles ? warp - kTiles : 0)) * kUnitsPerTile * 32 + lane;
   const int tile = warp < kTiles ? warp : warp - kTiles;
+  // Which warps own the tensor-core work.  The scheduler favours the HIGHER warp index (measured: the nine HMMA of the
+  // critical W_qV^T dq_V product on warps 0-6 took 840 cycles while warps 7-13 ran the deferred W_hh^T da product on the
+  // same pipes), so the products the step waits for sit on warps 7-13 and the deferred ones on warps 0-6.
+  const bool mmaCrit = warp >= kTiles && warp < 2 * kTiles, mmaDefer = warp < kTiles;
 
   // send the four values of a tile result to the owners of their hidden rows (reduce-scatter)
   auto scatter_tile = [&](const float (&o)[4], int xoff, uint32_t bar) {
@@ -384,9 +392,10 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     // ---- B2: partial dc_V (X_e) and the W_hh^T da piece of dh ----------------------------------------------
     // (the W_hh^T da piece of dh is not needed before B12: it runs later, in the shadow of the X_b exchange, so that
     //  the seven tiles of this critical product have the tensor pipe to themselves)
-    if (warp < kTiles) {
+    if (mmaCrit) {
       float o[4];
       mv_units<10>(w_tile + kUcV * 32, da_s + fg * kDaS + 2 * ft, o);
+      GSCAN3_STAMP(16);
       scatter_tile(o, L.xcV, 0);
     }
     GSCAN3_STAMP(4);
@@ -499,11 +508,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     io_store(dqV_s, kVs, 5, p.dqV, row0, kH, false);
     io_commit();   // the copies issued two barriers ago have landed; published by the barriers that follow
     // ---- B7: partial dq' = W_qV^T dq_V (X_b) ------------------------------------------------------------------------------
-    if (warp < kTiles) {
+    if (mmaCrit) {
       float o[4];
       mv_units<3>(w_tile + kUqV * 32, dqV_s + fg * kVs + 2 * ft, o);
+      GSCAN3_STAMP(17);
       scatter_tile(o, L.xqp, 2);
-    } else if (warp < 2 * kTiles) {
+    } else if (mmaDefer) {
       // the W_hh^T da piece of dh (da_s is untouched until the next cell backward), while X_b is in flight
       float o[4];
       mv_units<10>(w_tile + kUhh * 32, da_s + fg * kDaS + 2 * ft, o);
@@ -531,7 +541,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
       __syncthreads();
       io_store(dd_s, kVs, 5, p.dd, row0, kH, false);
       // ---- B9: the W_c[:, :H]^T dd piece of dh, and the partial dalpha completed with dd . P_cond (X_c) -------------
-      if (warp >= kTiles && warp < 2 * kTiles) {
+      if (mmaDefer) {
         float o[4];
         mv_units<3>(w_tile + kUc * 32, dd_s + fg * kVs + 2 * ft, o);
 #pragma unroll
@@ -540,8 +550,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
           if (h < kH) dhpart_s[(nF + (j & 1)) * kH + h] += o[j];
         }
       } else {
-        // warps 0-6 and 14-15: 9 warps, 4 lanes per (example, position) pair
-        const int w9 = warp < kTiles ? warp : warp - kTiles;
+        // warps 7-15: 9 warps, 4 lanes per (example, position) pair
+        const int w9 = warp - kTiles;
         const int total = kNB * Ti * 4;
         for (int base = w9 * 32; base < total; base += 9 * 32) {
           const int item = base + lane, pair = item >> 2, u = item & 3;
@@ -611,7 +621,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     }
     GSCAN3_STAMP(14);
     // ---- B12: last piece of dh, W_qT^T dq_T, added to the earlier pieces and reduce-scattered (X_d) ------------------------------
-    if (warp < kTiles) {
+    if (mmaCrit) {
       float o[4];
       mv_units<3>(w_tile + kUqT * 32, dqT_s + fg * kVs + 2 * ft, o);
 #pragma unroll
@@ -619,6 +629,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
         const int h = 16 * tile + fg + 8 * (j >> 1);
         if (h < kH) o[j] += dhpart_s[(nF + (j & 1)) * kH + h];
       }
+      GSCAN3_STAMP(18);
       scatter_tile(o, L.xdh, 4);
     }
     GSCAN3_STAMP(15);
