@@ -559,3 +559,29 @@ def test_alternative_schedules_keep_parity(env):
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "1 passed" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.parametrize("cfg_name,B", [("tiny", 5), ("comp", 4)])
+def test_dense_non_binary_situations(cfg_name, B):
+    """The situation CNN is a zero-skipping gather (gSCAN grids are {0,1} and ~3 % dense) but it must stay EXACT for any
+    input: dense, non-binary, negative situations through forward, loss and all gradients against the oracle."""
+    cfg = dict(O.CONFIGS[cfg_name])
+    cfg["auxiliary_task"] = True
+    params = O.synthetic_params(cfg, 41, scale=2.0)
+    batch = O.synthetic_batch(cfg, batch_size=B, seed=42, max_cmd_len=8, min_cmd_len=3, max_tgt_len=9)
+    rng = np.random.default_rng(43)
+    batch["situations"] = rng.normal(size=batch["situations"].shape).astype(np.float32)
+    batch["situations"][0] = 0.0          # and one all-zero grid
+    model = build_model(cfg, params, train=True)
+    d = to_dev(batch)
+    logp, aux = model(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"],
+                      situations_input=d["situations"], target_batch=d["targets"], target_lengths=batch["tgt_lengths"])
+    loss = model.get_loss(logp, d["targets"]) + 0.3 * model.get_auxiliary_loss(aux, d["positions"])
+    loss.backward()
+    logp_o, aux_o, loss_o, grads_o = oracle_run(cfg, params, batch)
+    assert (logp.detach().cpu().double() - logp_o).abs().max() <= LOGP_ATOL
+    assert (aux.detach().cpu().double() - aux_o).abs().max() <= LOGP_ATOL
+    named = dict(model.named_parameters())
+    for pname, _ in O.param_shapes(cfg):
+        err = rel_l2(named[pname].grad, grads_o[pname])
+        assert err <= GRAD_RTOL, f"{pname}: rel-L2 {err:.3e}"
