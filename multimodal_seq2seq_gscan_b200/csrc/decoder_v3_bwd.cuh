@@ -90,7 +90,14 @@ struct DecBwd3P {
   int t_signal[4];          // descending
 };
 
-// o = W_tile[16 x 8*NSTEPS] . x^T: fp32 fragments from shared memory, split into tf32 hi/lo on the fly
+// o = W_tile[16 x 8*NSTEPS] . x^T: fp32 fragments from shared memory, split into tf32 hi/lo on the fly.
+// Truncation split: the tensor core reads only the upper 19 bits of a tf32 operand, so the fp32 word ITSELF is the hi
+// operand (no instruction) and lo = x - trunc(x) costs one LOP + one FADD (round 1 rounded hi to nearest: three
+// instructions per element, ~2,400 warp-instructions per decoder step spent splitting constant weights).  |lo| < 2^-10 |x|
+// and the hardware truncates lo to 11 bits in turn: 2^-20 relative per product term instead of 2^-22.
+__device__ __forceinline__ uint32_t tf32_lo_trunc(float x) {
+  return __float_as_uint(x - __uint_as_float(__float_as_uint(x) & 0xffffe000u));
+}
 template <int NSTEPS>
 __device__ __forceinline__ void mv_units(const float4* __restrict__ w_lane, const float* __restrict__ x_lane,
                                          float (&o)[4]) {
@@ -99,11 +106,10 @@ __device__ __forceinline__ void mv_units(const float4* __restrict__ w_lane, cons
   for (int s = 0; s < NSTEPS; ++s) {
     const float2 xv = *reinterpret_cast<const float2*>(x_lane + 8 * s);
     const float4 a = w_lane[s * 32];
-    const uint32_t ah0 = tf32_hi(a.x), ah1 = tf32_hi(a.y), ah2 = tf32_hi(a.z), ah3 = tf32_hi(a.w);
-    const uint32_t al0 = __float_as_uint(a.x - __uint_as_float(ah0)), al1 = __float_as_uint(a.y - __uint_as_float(ah1)),
-                   al2 = __float_as_uint(a.z - __uint_as_float(ah2)), al3 = __float_as_uint(a.w - __uint_as_float(ah3));
-    const uint32_t bh0 = tf32_hi(xv.x), bh1 = tf32_hi(xv.y);
-    const uint32_t bl0 = __float_as_uint(xv.x - __uint_as_float(bh0)), bl1 = __float_as_uint(xv.y - __uint_as_float(bh1));
+    const uint32_t ah0 = __float_as_uint(a.x), ah1 = __float_as_uint(a.y), ah2 = __float_as_uint(a.z), ah3 = __float_as_uint(a.w);
+    const uint32_t al0 = tf32_lo_trunc(a.x), al1 = tf32_lo_trunc(a.y), al2 = tf32_lo_trunc(a.z), al3 = tf32_lo_trunc(a.w);
+    const uint32_t bh0 = __float_as_uint(xv.x), bh1 = __float_as_uint(xv.y);
+    const uint32_t bl0 = tf32_lo_trunc(xv.x), bl1 = tf32_lo_trunc(xv.y);
     mma_tf32(d0, ah0, ah1, ah2, ah3, bh0, bh1);
     mma_tf32(d1, al0, al1, al2, al3, bh0, bh1);
     mma_tf32(d2, ah0, ah1, ah2, ah3, bl0, bl1);
