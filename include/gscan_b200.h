@@ -215,6 +215,30 @@ int gscan_metrics(const float* logp, const int64_t* targets, int32_t B, int32_t 
                   int32_t pad_idx, int32_t* counts /* [3] */, void* stream);
 
 /*
+ * Dropout drawn inside the kernels (new; the reference draws its masks with three nn.Dropout modules per step:
+ * cnn_model.py:31, seq2seq_model.py:59,385).  gscan_forward_rng / gscan_backward_rng are gscan_forward / gscan_backward
+ * without mask arguments: every dropout site (0 CNN features [B, G*G, 3F], 1 command embeddings [B, Ti, E], 2 target
+ * embeddings [B, Tt, H]) takes element i of its mask from a Philox4x32-10 stream keyed by (seed, offset, site) - keep
+ * with probability 1 - p, scale by 1 / (1 - p).  The backward call must get the SAME gscan_dropout as its forward call.
+ * Advance `offset` by one per training step.  gscan_dropout_mask writes the n mask values of one site (parity tests:
+ * the materialised masks passed to gscan_forward / gscan_backward give bit-identical results).
+ */
+typedef struct gscan_dropout {
+  float p_cnn, p_enc, p_dec;
+  uint64_t seed, offset;
+} gscan_dropout;
+int gscan_forward_rng(const gscan_dims* d, const float* const* params,
+                      const int64_t* commands, const int32_t* cmd_len, const float* situations,
+                      const int64_t* targets, const gscan_dropout* rng,
+                      float* workspace, size_t workspace_floats, float* logp, float* aux_logp, void* stream);
+int gscan_backward_rng(const gscan_dims* d, const float* const* params,
+                       const int64_t* commands, const int32_t* cmd_len, const float* situations,
+                       const int64_t* targets, const gscan_dropout* rng,
+                       float* workspace, size_t workspace_floats, const float* d_logp, const float* d_aux_logp,
+                       float* const* grads, void* stream);
+int gscan_dropout_mask(const gscan_dropout* rng, int32_t which, size_t n, float* out, void* stream);
+
+/*
  * Fused Adam over a flat parameter/gradient buffer (what torch.optim.Adam does per tensor in
  * reference train.py:67-70,110-113, with the LambdaLR factor folded into `lr`):
  *   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr/(1-b1^t) * m / (sqrt(v/(1-b2^t)) + eps)

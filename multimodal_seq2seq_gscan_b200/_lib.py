@@ -32,6 +32,12 @@ class Dims(ctypes.Structure):
         "auxiliary_task", "pad_idx_in", "pad_idx_out", "Ti_stride")]
 
 
+class Dropout(ctypes.Structure):
+    """Mirror of ``gscan_dropout``: dropout drawn inside the kernels from a Philox stream keyed by (seed, offset, site)."""
+    _fields_ = [("p_cnn", c_float), ("p_enc", c_float), ("p_dec", c_float), ("seed", ctypes.c_uint64),
+                ("offset", ctypes.c_uint64)]
+
+
 ParamArray = c_void_p * NUM_PARAMS
 
 # name -> (restype, argtypes); exactly the symbols include/gscan_b200.h declares
@@ -50,6 +56,12 @@ SIGNATURES = {
     "gscan_backward": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
                                  POINTER(ParamArray), c_void_p]),
+    "gscan_forward_rng": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p,
+                                    POINTER(Dropout), c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "gscan_backward_rng": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p,
+                                     POINTER(Dropout), c_void_p, c_size_t, c_void_p, c_void_p, POINTER(ParamArray),
+                                     c_void_p]),
+    "gscan_dropout_mask": (c_int32, [POINTER(Dropout), c_int32, c_size_t, c_void_p, c_void_p]),
     "gscan_encode": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gscan_decoder_step": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p,

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) cnn_forward_kernel(CnnShape s, const floa
                                                           const float* __restrict__ b1,
                                                           const float* __restrict__ b2,
                                                           const float* __restrict__ b3,
-                                                          const float* __restrict__ drop,
+                                                          DropSrc drop,
                                                           float* __restrict__ feat) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int M = s.M(), D = s.D(), MC = M * s.C;
@@ -119,18 +119,18 @@ __global__ void __launch_bounds__(256) cnn_forward_kernel(CnnShape s, const floa
     }
     acc = fmaxf(acc, 0.f);
     long oi = (long)b * M * D + o;
-    if (drop) acc *= __ldg(drop + oi);
+    if (drop.active()) acc *= drop_at(drop, oi);
     feat[oi] = acc;
   }
 }
 
 // dconv = dfeat * [feat > 0] * dropmask   (ReLU + dropout backward), elementwise
 __global__ void cnn_dact_kernel(const float* __restrict__ dfeat, const float* __restrict__ feat,
-                                const float* __restrict__ drop, float* __restrict__ dconv, long n) {
+                                DropSrc drop, float* __restrict__ dconv, long n) {
   long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g = feat[i] > 0.f ? dfeat[i] : 0.f;
-  if (drop) g *= drop[i];
+  if (drop.active()) g *= drop_at(drop, i);
   dconv[i] = g;
 }
 

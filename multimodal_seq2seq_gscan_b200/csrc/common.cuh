@@ -74,6 +74,47 @@ __device__ __forceinline__ void act_tanh_n(const float (&x)[N], float (&y)[N]) {
 }
 #endif
 
+// ---- dropout masks: explicit (parity tests, the oracle's masks) or drawn in the consuming kernel -------------------
+// Round 1 drew the three masks of a step with three ATen kernels before the forward pass and read them back in five
+// kernels (25 MB per step through HBM).  A DropSrc names the mask of one dropout site instead: either a pointer to an
+// explicit, already scaled mask, or a Philox4x32-10 stream (key = seed, counter = element index / 4, site, call
+// number): the forward and the backward kernels of a step regenerate the same bits from the same counter.
+struct DropSrc {
+  const float* mask = nullptr;
+  unsigned int k0 = 0, k1 = 0, c2 = 0, c3 = 0;
+  unsigned int thresh = 0;   // keep iff the 32 random bits are >= thresh (= p * 2^32)
+  float scale = 1.f;         // 1 / (1 - p)
+  int rng = 0;
+  __host__ __device__ DropSrc() {}
+  __host__ __device__ DropSrc(const float* m) : mask(m) {}
+  __host__ __device__ bool active() const { return mask != nullptr || rng != 0; }
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int h0 = __umulhi(0xD2511F53u, c.x), l0 = 0xD2511F53u * c.x;
+    const unsigned int h1 = __umulhi(0xCD9E8D57u, c.z), l1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(h1 ^ c.y ^ k.x, l1, h0 ^ c.w ^ k.y, l0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// mask values of the four elements i .. i + 3 (i a multiple of 4)
+__device__ __forceinline__ float4 drop_at4(const DropSrc& d, long i) {
+  if (d.mask) return __ldg(reinterpret_cast<const float4*>(d.mask + i));
+  const uint4 r = philox4x32_10(make_uint4((unsigned int)(i >> 2), (unsigned int)(i >> 34), d.c2, d.c3), make_uint2(d.k0, d.k1));
+  return make_float4(r.x >= d.thresh ? d.scale : 0.f, r.y >= d.thresh ? d.scale : 0.f, r.z >= d.thresh ? d.scale : 0.f,
+                     r.w >= d.thresh ? d.scale : 0.f);
+}
+__device__ __forceinline__ float drop_at(const DropSrc& d, long i) {
+  if (d.mask) return __ldg(d.mask + i);
+  const uint4 r = philox4x32_10(make_uint4((unsigned int)(i >> 2), (unsigned int)(i >> 34), d.c2, d.c3), make_uint2(d.k0, d.k1));
+  const int j = (int)(i & 3);
+  const unsigned int v = j == 0 ? r.x : (j == 1 ? r.y : (j == 2 ? r.z : r.w));
+  return v >= d.thresh ? d.scale : 0.f;
+}
+
 // Packed fp32 FMA (FFMA2, new on sm_100): two independent IEEE fp32 FMAs per issue slot.
 __device__ __forceinline__ void fma2(float2& acc, const float2 a, const float2 b) {
   acc = __ffma2_rn(a, b, acc);

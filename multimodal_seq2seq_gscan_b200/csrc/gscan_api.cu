@@ -393,7 +393,7 @@ int matmul_nn(const float* A, long lda, const float* W, long ldw, float* C, long
   return launch_gemm(A, lda, 1, W, ldw, 1, C, ldc, M, N, K, nullptr, nullptr, 0, accumulate, 1, st);
 }
 
-int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* situations, const float* drop_cnn,
+int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* situations, DropSrc drop_cnn,
                     float* Wt, float* feat, cudaStream_t st) {
   CnnShape cs{d.B, d.G, d.C, d.F, d.K3};
   cnn_relayout_kernel<<<ceil_div(cs.wtotal(), 256), 256, 0, st>>>(
@@ -413,7 +413,7 @@ int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* sit
 // The encoder chain runs on `st`.  The CNN chain runs on `cnn_stream` when the caller passes one (and then orders it
 // itself), else on helper stream 0, forked from and joined back into `st` here.
 int run_encoder_side(const gscan_dims& d, const float* const* P, const long long* commands, const int* cmd_len,
-                     const float* situations, const float* drop_cnn, const float* drop_enc, float* ws,
+                     const float* situations, DropSrc drop_cnn, DropSrc drop_enc, float* ws,
                      const Layout& L, bool need_keys, cudaStream_t st, cudaStream_t cnn_stream = nullptr,
                      bool cnn_stream_given = false) {
   const int B = d.B, Ti = d.Ti, M = d.G * d.G, D = 3 * d.F, H = d.H, E = d.E;
@@ -840,6 +840,31 @@ int launch_dec_bwd_v3(const gscan_dims& d, v3::DecBwd3P p, cudaStream_t st) {
   return 0;
 }
 
+// the DropSrc of dropout site `which` (0 CNN features, 1 command embeddings, 2 target embeddings): an explicit mask, or the
+// Philox stream of (seed, call offset, site)
+DropSrc make_drop(const float* mask, const gscan_dropout* rng, int which) {
+  DropSrc d(mask);
+  if (mask != nullptr || rng == nullptr) return d;
+  const float p = which == 0 ? rng->p_cnn : (which == 1 ? rng->p_enc : rng->p_dec);
+  if (!(p > 0.f)) return d;
+  d.rng = 1;
+  d.k0 = (unsigned int)rng->seed;
+  d.k1 = (unsigned int)(rng->seed >> 32) ^ (unsigned int)(rng->offset >> 32);
+  d.c2 = (unsigned int)which;
+  d.c3 = (unsigned int)rng->offset;
+  const double t = (double)p * 4294967296.0;
+  d.thresh = t >= 4294967295.0 ? 0xffffffffu : (unsigned int)t;
+  d.scale = 1.f / (1.f - p);
+  return d;
+}
+
+int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                 const float* situations, const int64_t* targets, DropSrc drop_cnn, DropSrc drop_enc, DropSrc drop_dec,
+                 float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream);
+int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                  const float* situations, const int64_t* targets, DropSrc drop_cnn, DropSrc drop_enc, DropSrc drop_dec,
+                  float* ws, size_t ws_floats, const float* d_logp, const float* d_aux_logp, float* const* G, void* stream);
+
 }  // namespace
 
 // =================================================================================================
@@ -909,6 +934,43 @@ size_t gscan_greedy_workspace_floats(const gscan_dims* d) {
 int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
                   const float* situations, const int64_t* targets, const float* drop_cnn, const float* drop_enc,
                   const float* drop_dec, float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream) {
+  return forward_impl(d, P, commands, cmd_len, situations, targets, DropSrc(drop_cnn), DropSrc(drop_enc), DropSrc(drop_dec), ws,
+                      ws_floats, logp, aux_logp, stream);
+}
+
+int gscan_forward_rng(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                      const float* situations, const int64_t* targets, const gscan_dropout* rng, float* ws,
+                      size_t ws_floats, float* logp, float* aux_logp, void* stream) {
+  return forward_impl(d, P, commands, cmd_len, situations, targets, make_drop(nullptr, rng, 0), make_drop(nullptr, rng, 1),
+                      make_drop(nullptr, rng, 2), ws, ws_floats, logp, aux_logp, stream);
+}
+
+int gscan_backward_rng(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                       const float* situations, const int64_t* targets, const gscan_dropout* rng, float* ws,
+                       size_t ws_floats, const float* d_logp, const float* d_aux_logp, float* const* G, void* stream) {
+  return backward_impl(d, P, commands, cmd_len, situations, targets, make_drop(nullptr, rng, 0), make_drop(nullptr, rng, 1),
+                       make_drop(nullptr, rng, 2), ws, ws_floats, d_logp, d_aux_logp, G, stream);
+}
+
+int gscan_dropout_mask(const gscan_dropout* rng, int32_t which, size_t n, float* out, void* stream) {
+  if (!rng || !out || which < 0 || which > 2) return GSCAN_E_BADARG;
+  if (n == 0) return GSCAN_OK;
+  DropSrc src = make_drop(nullptr, rng, which);
+  if (!src.rng) {   // p == 0: the mask is all ones
+    src.rng = 1; src.thresh = 0; src.scale = 1.f;
+  }
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, out, (long)n);
+  GSCAN_CHECK_LAUNCH();
+  return GSCAN_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                 const float* situations, const int64_t* targets, DropSrc drop_cnn, DropSrc drop_enc, DropSrc drop_dec,
+                 float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream) {
   TRY(check_common(d, P));
   if (!commands || !cmd_len || !situations || !targets || !ws || !logp) return GSCAN_E_BADARG;
   if (d->auxiliary_task && !aux_logp) return GSCAN_E_BADARG;
@@ -938,7 +1000,7 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
   {
     long n = (long)B * Tt * H;
-    const bool vec4 = (H & 3) == 0 && aligned16(P[GSCAN_P_DEC_EMB]) && (!drop_dec || aligned16(drop_dec));
+    const bool vec4 = (H & 3) == 0 && aligned16(P[GSCAN_P_DEC_EMB]) && (!drop_dec.mask || aligned16(drop_dec.mask));
     if (vec4)
       embed4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, sp>>>(tgts, Tt, P[GSCAN_P_DEC_EMB], H, drop_dec, ws + L.U,
                                                                      4 * H, B, Tt, 1);
@@ -1030,10 +1092,25 @@ int gscan_forward(const gscan_dims* d, const float* const* P, const int64_t* com
   return GSCAN_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
 int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
                    const float* situations, const int64_t* targets, const float* drop_cnn, const float* drop_enc,
                    const float* drop_dec, float* ws, size_t ws_floats, const float* d_logp, const float* d_aux_logp,
                    float* const* G, void* stream) {
+  return backward_impl(d, P, commands, cmd_len, situations, targets, DropSrc(drop_cnn), DropSrc(drop_enc), DropSrc(drop_dec), ws,
+                       ws_floats, d_logp, d_aux_logp, G, stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                  const float* situations, const int64_t* targets, DropSrc drop_cnn, DropSrc drop_enc, DropSrc drop_dec,
+                  float* ws, size_t ws_floats, const float* d_logp, const float* d_aux_logp, float* const* G, void* stream) {
   TRY(check_common(d, P));
   if (!commands || !cmd_len || !situations || !targets || !ws || !d_logp || !G) return GSCAN_E_BADARG;
   for (int i = 0; i < GSCAN_NUM_PARAMS; ++i) {
@@ -1410,6 +1487,10 @@ int gscan_backward(const gscan_dims* d, const float* const* P, const int64_t* co
   chain_report("backward after the sweep");
   return GSCAN_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int gscan_encode(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
                  const float* situations, const float* drop_cnn, const float* drop_enc, float* ws, size_t ws_floats,

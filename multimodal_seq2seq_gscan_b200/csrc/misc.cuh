@@ -44,7 +44,7 @@ inline int launch_pack(const PackTable& tab, cudaStream_t st) {
 //                         rows, group 0 reserved), mask row = b*T + t
 // ---------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const long long* __restrict__ tokens, int tok_stride, const float* __restrict__ W,
-                             int Wd, const float* __restrict__ mask, float* __restrict__ out, long ldo,
+                             int Wd, DropSrc mask, float* __restrict__ out, long ldo,
                              int B, int T, int row_mode) {
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long)B * T * Wd) return;
@@ -53,14 +53,14 @@ __global__ void embed_kernel(const long long* __restrict__ tokens, int tok_strid
   int b = r / T, t = r - (long)b * T;
   long long tok = tokens[(long)b * tok_stride + t];
   float v = __ldg(W + tok * Wd + h);
-  if (mask) v *= __ldg(mask + r * Wd + h);
+  if (mask.active()) v *= drop_at(mask, r * Wd + h);
   long orow = row_mode == 0 ? r : ((long)(t + 1) * B + b);
   out[orow * ldo + h] = v;
 }
 
 // 4 elements per thread (Wd % 4 == 0, 16-byte aligned rows): a quarter of the threads and 128-bit accesses
 __global__ void embed4_kernel(const long long* __restrict__ tokens, int tok_stride, const float* __restrict__ W,
-                              int Wd, const float* __restrict__ mask, float* __restrict__ out, long ldo,
+                              int Wd, DropSrc mask, float* __restrict__ out, long ldo,
                               int B, int T, int row_mode) {
   const int Wq = Wd >> 2;
   long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,8 +70,8 @@ __global__ void embed4_kernel(const long long* __restrict__ tokens, int tok_stri
   int b = r / T, t = r - (long)b * T;
   long long tok = tokens[(long)b * tok_stride + t];
   float4 v = __ldg(reinterpret_cast<const float4*>(W + tok * Wd) + hq);
-  if (mask) {
-    const float4 m = __ldg(reinterpret_cast<const float4*>(mask + r * Wd) + hq);
+  if (mask.active()) {
+    const float4 m = drop_at4(mask, r * Wd + 4 * hq);
     v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
   }
   long orow = row_mode == 0 ? r : ((long)(t + 1) * B + b);
@@ -87,7 +87,7 @@ __host__ __device__ inline int embed_bwd_groups(int Wd, int nthreads) { return W
 
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restrict__ tokens, int tok_stride,
                                                         const float* __restrict__ dX, long ldx,
-                                                        const float* __restrict__ mask, float* __restrict__ dW,
+                                                        DropSrc mask, float* __restrict__ dW,
                                                         int Wd, int Vsz, int pad, int B, int T, int row_mode,
                                                         int rows_per_block, int use_smem) {
   extern __shared__ __align__(16) float acc_s[];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
             if (tok[u] != pad) {
               const long xrow = row_mode == 0 ? r : ((long)t * B + b);
               x[u] = __ldg(dX + xrow * ldx + h);
-              if (mask) x[u] *= __ldg(mask + r * Wd + h);
+              if (mask.active()) x[u] *= drop_at(mask, r * Wd + h);
             }
           }
         }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
     long xrow = row_mode == 0 ? r : ((long)t * B + b);
     for (int h = lane; h < Wd; h += 32) {
       float g = __ldg(dX + xrow * ldx + h);
-      if (mask) g *= __ldg(mask + r * Wd + h);
+      if (mask.active()) g *= drop_at(mask, r * Wd + h);
       atomicAdd(dW + tok * Wd + h, g);
     }
   }
@@ -434,6 +434,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   v[i] = vi;
   float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] -= (lr / bc1) * (mi / denom);
+}
+
+// the mask of a dropout site, materialised (parity tests of the in-kernel draw)
+__global__ void dropout_mask_kernel(DropSrc src, float* __restrict__ out, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = drop_at(src, i);
 }
 
 // d_pre = d_out * (1 - out^2)

@@ -294,7 +294,8 @@ class Model(nn.Module):
         Ti = ops.max_length(commands_lengths)
         Tt = target_batch.shape[1]
         cmd_len = ops.lengths_to_device(commands_lengths, dev)
-        masks = self._masks(B, G, Ti, Tt, dev)
+        # training: the dropout of the three sites is drawn inside the kernels (no mask tensors, no ATen launches)
+        masks = (ops.dropout_rng(*self._dropout_p) if self.training else None) or (None, None, None)
         logp, aux = ops.ModelForward.apply(self._cfg(G), commands_input, cmd_len, Ti, situations_input, target_batch,
                                            masks, *self._param_list())
         if not self.auxiliary_task:

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Dims, ParamArray
+from ._lib import Dims, Dropout, ParamArray
 
 # launches issued by the library since import, for bench.py's "gpu_launches" claim
 _call_counts = {"forward": 0, "backward": 0, "greedy": 0, "other": 0}
@@ -87,8 +87,37 @@ def _dropout_mask(shape, p: float, device, generator=None) -> Optional[torch.Ten
     return mask.mul_(1.0 / (1.0 - p))
 
 
+_rng_calls = 0
+
+
+def dropout_rng(p_cnn: float, p_enc: float, p_dec: float) -> Optional[Dropout]:
+    """The dropout of ONE training step, drawn inside the kernels: a Philox stream keyed by torch's seed (mixed with
+    the rank under torch.distributed, so that replicas draw different masks) and a per-process step counter.  No
+    device work, no host sync.  None when all probabilities are zero."""
+    global _rng_calls
+    if p_cnn <= 0 and p_enc <= 0 and p_dec <= 0:
+        return None
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        seed = (seed + 0x9E3779B97F4A7C15 * (torch.distributed.get_rank() + 1)) & 0xFFFFFFFFFFFFFFFF
+    _rng_calls += 1
+    return Dropout(float(p_cnn), float(p_enc), float(p_dec), seed, _rng_calls)
+
+
+def dropout_masks_of(rng: Dropout, shapes, device) -> list:
+    """The three masks a ``Dropout`` stands for, materialised (tests): shapes = ((B, M, 3F), (B, Ti, E), (B, Tt, H))."""
+    lib = _lib.load()
+    out = []
+    for which, shape in enumerate(shapes):
+        m = torch.empty(shape, dtype=torch.float32, device=device)
+        _lib.check(lib.gscan_dropout_mask(rng, which, m.numel(), _ptr(m), _stream(device)), "gscan_dropout_mask")
+        out.append(m)
+    return out
+
+
 class ModelForward(torch.autograd.Function):
-    """(logp [B,Tt,V], aux_logp [B,M]) = gscan_forward(...); backward = gscan_backward(...)."""
+    """(logp [B,Tt,V], aux_logp [B,M]) = gscan_forward(...); backward = gscan_backward(...).  ``masks`` is a triple of
+    explicit dropout masks (or Nones), or a ``Dropout`` (masks drawn inside the kernels: gscan_forward_rng)."""
 
     @staticmethod
     def forward(ctx, cfg, commands, cmd_len_dev, Ti, situations, targets, masks, *params):
@@ -107,10 +136,16 @@ class ModelForward(torch.autograd.Function):
         logp = torch.empty(B, Tt, dims.V, dtype=torch.float32, device=dev)
         aux = torch.empty(B, M, dtype=torch.float32, device=dev) if dims.auxiliary_task else None
         parr = _param_array([None if p is None else p.detach() for p in params])
-        drop_cnn, drop_enc, drop_dec = masks
-        rc = lib.gscan_forward(dims, parr, _ptr(commands), _ptr(cmd_len_dev), _ptr(situations), _ptr(targets),
-                               _ptr(drop_cnn), _ptr(drop_enc), _ptr(drop_dec), _ptr(ws), n_ws, _ptr(logp), _ptr(aux),
-                               _stream(dev))
+        ctx.rng = masks if isinstance(masks, Dropout) else None
+        if ctx.rng is not None:
+            rc = lib.gscan_forward_rng(dims, parr, _ptr(commands), _ptr(cmd_len_dev), _ptr(situations), _ptr(targets),
+                                       ctx.rng, _ptr(ws), n_ws, _ptr(logp), _ptr(aux), _stream(dev))
+            masks = (None, None, None)
+        else:
+            drop_cnn, drop_enc, drop_dec = masks
+            rc = lib.gscan_forward(dims, parr, _ptr(commands), _ptr(cmd_len_dev), _ptr(situations), _ptr(targets),
+                                   _ptr(drop_cnn), _ptr(drop_enc), _ptr(drop_dec), _ptr(ws), n_ws, _ptr(logp),
+                                   _ptr(aux), _stream(dev))
         _lib.check(rc, "gscan_forward")
         _call_counts["forward"] += 1
         ctx.dims = dims
@@ -157,9 +192,14 @@ class ModelForward(torch.autograd.Function):
             flat[:n_flat].zero_()      # the tail (data-parallel counts) belongs to the caller
         views = [None if s is None else flat[int(o):int(o) + n].view(s)
                  for s, o, n in zip(ctx.param_shapes, offsets[:-1], sizes)]
-        rc = lib.gscan_backward(dims, _param_array(params), _ptr(commands), _ptr(cmd_len_dev), _ptr(situations),
-                                _ptr(targets), _ptr(masks[0]), _ptr(masks[1]), _ptr(masks[2]), _ptr(ws), ctx.n_ws,
-                                _ptr(d_logp), _ptr(d_aux), _param_array(views), _stream(dev))
+        if ctx.rng is not None:
+            rc = lib.gscan_backward_rng(dims, _param_array(params), _ptr(commands), _ptr(cmd_len_dev), _ptr(situations),
+                                        _ptr(targets), ctx.rng, _ptr(ws), ctx.n_ws, _ptr(d_logp), _ptr(d_aux),
+                                        _param_array(views), _stream(dev))
+        else:
+            rc = lib.gscan_backward(dims, _param_array(params), _ptr(commands), _ptr(cmd_len_dev), _ptr(situations),
+                                    _ptr(targets), _ptr(masks[0]), _ptr(masks[1]), _ptr(masks[2]), _ptr(ws), ctx.n_ws,
+                                    _ptr(d_logp), _ptr(d_aux), _param_array(views), _stream(dev))
         _lib.check(rc, "gscan_backward")
         _call_counts["backward"] += 1
         return (None, None, None, None, None, None, None, *views)

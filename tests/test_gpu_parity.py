@@ -585,3 +585,44 @@ def test_dense_non_binary_situations(cfg_name, B):
     for pname, _ in O.param_shapes(cfg):
         err = rel_l2(named[pname].grad, grads_o[pname])
         assert err <= GRAD_RTOL, f"{pname}: rel-L2 {err:.3e}"
+
+
+def test_in_kernel_dropout_matches_materialised_masks():
+    """Training-mode dropout is drawn inside the kernels (Philox stream per site, gscan_forward_rng / _backward_rng).
+    The masks such a stream stands for can be materialised (gscan_dropout_mask): passing THEM explicitly gives the same
+    log-probs and gradients, and the oracle with those masks agrees - so the in-kernel draw is covered by the same
+    parity bar as everything else.  Also: kept fraction, scale, independence of the call counter."""
+    cfg = dict(O.CONFIGS["comp"])
+    cfg["auxiliary_task"] = True
+    params = O.synthetic_params(cfg, 21, scale=2.0)
+    B = 7
+    batch = O.synthetic_batch(cfg, batch_size=B, seed=22, max_cmd_len=8, min_cmd_len=3, max_tgt_len=25)
+    Ti, Tt = batch["commands"].shape[1], batch["targets"].shape[1]
+    M, D, E, H = cfg["grid_size"] ** 2, 3 * cfg["cnn_hidden_num_channels"], cfg["embedding_dimension"], cfg["decoder_hidden_size"]
+    rng = ops.Dropout(0.1, 0.3, 0.3, 1234, 7)
+    masks = ops.dropout_masks_of(rng, ((B, M, D), (B, Ti, E), (B, Tt, H)), DEV)
+    for m, p in zip(masks, (0.1, 0.3, 0.3)):
+        vals = torch.unique(m).cpu().tolist()
+        assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1 / (1 - p)) < 1e-6
+        assert abs((m > 0).float().mean().item() - (1 - p)) < 0.03
+    other = ops.dropout_masks_of(ops.Dropout(0.1, 0.3, 0.3, 1234, 8), ((B, M, D), (B, Ti, E), (B, Tt, H)), DEV)
+    assert not torch.equal(other[2], masks[2])
+    d = to_dev(batch)
+    cmd_len = ops.lengths_to_device(batch["cmd_lengths"], DEV)
+    results = []
+    for how in (rng, tuple(masks)):
+        model = build_model(cfg, params, train=True)
+        logp, aux = ops.ModelForward.apply(model._cfg(cfg["grid_size"]), d["commands"], cmd_len, Ti, d["situations"],
+                                           d["targets"], how, *model._param_list())
+        loss = model.get_loss(logp, d["targets"]) + 0.3 * model.get_auxiliary_loss(aux, d["positions"])
+        loss.backward()
+        results.append((logp.detach(), aux.detach(), {n: p.grad.detach() for n, p in model.named_parameters()}))
+    (lp_a, aux_a, g_a), (lp_b, aux_b, g_b) = results
+    assert torch.equal(lp_a, lp_b) and torch.equal(aux_a, aux_b)
+    for name in g_a:      # (split-K atomics: equal up to summation order)
+        assert rel_l2(g_a[name], g_b[name]) <= 1e-6, name
+    logp_o, aux_o, loss_o, grads_o = oracle_run(cfg, params, batch,
+                                                dropout={"cnn": masks[0].cpu(), "enc": masks[1].cpu(), "dec": masks[2].cpu()})
+    assert (lp_a.cpu().double() - logp_o).abs().max() <= LOGP_ATOL
+    for pname, _ in O.param_shapes(cfg):
+        assert rel_l2(g_a[pname], grads_o[pname]) <= GRAD_RTOL, pname
