@@ -193,14 +193,16 @@ int gscan_greedy_decode(const gscan_dims* d, const float* const* params,
 /*
  * NLLLoss(ignore_index = pad_idx), mean over the non-ignored entries, of logp [B,Tt,V] against
  * targets [B,Tt] shifted left by `shift`: entry (b,t) is scored against targets[b, t+shift], entries
- * with t+shift >= Tt are ignored.
+ * with t+shift >= Tt hold the literal 0 the reference appends (ignored when pad_idx == 0, scored as class 0 otherwise).
  *   shift = 1: Model.get_loss (reference model.py:108-115,147-160: drop SOS, append a pad);
  *   shift = 0, Tt = 1, pad_idx = -100: Model.get_auxiliary_loss (model.py:59,162-164).
- * loss_out[0] = mean NLL, loss_out[1] = number of scored entries (as float).
+ * loss_out[0] = mean NLL, loss_out[1] = number of scored entries (as float); loss_out must hold
+ * GSCAN_NLL_OUT_FLOATS floats (the rest is scratch of the fixed-order two-stage reduction).
  * gscan_nll_backward writes d_logp = d_loss * dNLL/dlogp (dense, overwritten).
  */
+#define GSCAN_NLL_OUT_FLOATS 68
 int gscan_nll_forward(const float* logp, const int64_t* targets, int32_t B, int32_t Tt, int32_t V,
-                      int32_t pad_idx, int32_t shift, float* loss_out /* [2] */, void* stream);
+                      int32_t pad_idx, int32_t shift, float* loss_out /* [GSCAN_NLL_OUT_FLOATS] */, void* stream);
 int gscan_nll_backward(const int64_t* targets, int32_t B, int32_t Tt, int32_t V, int32_t pad_idx,
                        int32_t shift, const float* loss_out /* [2] from forward */,
                        const float* d_loss /* [1] */, float* d_logp /* [B,Tt,V], overwritten */,

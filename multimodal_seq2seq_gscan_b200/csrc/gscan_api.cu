@@ -1633,8 +1633,11 @@ int gscan_greedy_decode(const gscan_dims* d, const float* const* P, const int64_
 int gscan_nll_forward(const float* logp, const int64_t* targets, int32_t B, int32_t Tt, int32_t V, int32_t pad_idx,
                       int32_t shift, float* loss_out, void* stream) {
   if (!logp || !targets || !loss_out || B < 1 || Tt < 1 || V < 1 || shift < 0) return GSCAN_E_BADARG;
-  nll_forward_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logp, reinterpret_cast<const long long*>(targets), B, Tt, V,
-                                                          pad_idx, shift, loss_out);
+  static_assert(kNllBlocks <= 32 && 2 + 2 * kNllBlocks <= GSCAN_NLL_OUT_FLOATS, "scratch behind loss_out");
+  nll_forward_kernel<<<kNllBlocks, 256, 0, (cudaStream_t)stream>>>(logp, reinterpret_cast<const long long*>(targets), B, Tt,
+                                                                  V, pad_idx, shift, loss_out + 2);
+  GSCAN_CHECK_LAUNCH();
+  nll_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_out, kNllBlocks);
   GSCAN_CHECK_LAUNCH();
   return GSCAN_OK;
 }

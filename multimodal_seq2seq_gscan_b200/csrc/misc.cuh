@@ -327,22 +327,24 @@ __global__ void __launch_bounds__(256) row_logsoftmax_bwd_kernel(const float* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// Loss / metrics (model.py:108-160): targets shifted left by one, pad ignored.  Single CTA,
-// fixed-order tree reduction => bitwise reproducible.
+// Loss / metrics (model.py:108-160): targets shifted left by one, pad ignored.  kNllBlocks CTAs write partial
+// (sum, count) pairs, one warp adds them in a fixed order => bitwise reproducible (round 1: a single CTA walked all
+// B * Tt rows, 16 us on the path between the forward and the backward pass).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) nll_forward_kernel(const float* __restrict__ logp, const long long* __restrict__ tgt,
-                                                           int B, int T, int V, int pad, int shift,
-                                                           float* __restrict__ out) {
+constexpr int kNllBlocks = 32;
+__global__ void __launch_bounds__(256) nll_forward_kernel(const float* __restrict__ logp, const long long* __restrict__ tgt,
+                                                          int B, int T, int V, int pad, int shift,
+                                                          float* __restrict__ partial /* [gridDim.x][2] */) {
   __shared__ float s_sum[32];
   __shared__ float s_cnt[32];
   float sum = 0.f, cnt = 0.f;
   const long R = (long)B * T;
-  constexpr int kU = 8;   // rows in flight per thread: all targets first, then all log-probs (two dependent latencies per pass)
-  for (long rb = threadIdx.x; rb < R; rb += (long)kU * blockDim.x) {
+  constexpr int kU = 4;   // rows in flight per thread: all targets first, then all log-probs (two dependent latencies per pass)
+  for (long rb = (long)blockIdx.x * blockDim.x + threadIdx.x; rb < R; rb += (long)kU * blockDim.x * gridDim.x) {
     long long y[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const long r = rb + (long)u * blockDim.x;
+      const long r = rb + (long)u * blockDim.x * gridDim.x;
       y[u] = pad;
       if (r < R) {
         int b = r / T, t = r - (long)b * T;
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(1024) nll_forward_kernel(const float* __restri
     float lp[kU];
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
-      const long r = rb + (long)u * blockDim.x;
+      const long r = rb + (long)u * blockDim.x * gridDim.x;
       lp[u] = y[u] != pad ? __ldg(logp + r * V + y[u]) : 0.f;
     }
 #pragma unroll
@@ -369,8 +371,15 @@ __global__ void __launch_bounds__(1024) nll_forward_kernel(const float* __restri
     sum = threadIdx.x < nw ? s_sum[threadIdx.x] : 0.f;
     cnt = threadIdx.x < nw ? s_cnt[threadIdx.x] : 0.f;
     sum = warp_sum(sum); cnt = warp_sum(cnt);
-    if (threadIdx.x == 0) { out[0] = sum / cnt; out[1] = cnt; }
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sum; partial[2 * blockIdx.x + 1] = cnt; }
   }
+}
+// out[0] = mean, out[1] = count from the partial pairs behind them (out + 2): one warp, fixed order
+__global__ void nll_final_kernel(float* __restrict__ out, int nblocks) {
+  const int lane = threadIdx.x;
+  float sum = lane < nblocks ? out[2 + 2 * lane] : 0.f, cnt = lane < nblocks ? out[3 + 2 * lane] : 0.f;
+  sum = warp_sum(sum); cnt = warp_sum(cnt);
+  if (lane == 0) { out[0] = sum / cnt; out[1] = cnt; }
 }
 
 __global__ void nll_backward_kernel(const long long* __restrict__ tgt, int B, int T, int V, int pad, int shift,

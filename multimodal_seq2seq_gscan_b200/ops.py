@@ -88,6 +88,16 @@ def _dropout_mask(shape, p: float, device, generator=None) -> Optional[torch.Ten
 
 
 _rng_calls = 0
+_ZEROS1: dict = {}
+
+
+def _zeros1(dev) -> torch.Tensor:
+    """A fresh view of a per-device constant zeros(1) (the placeholder auxiliary output): no fill kernel per step."""
+    z = _ZEROS1.get(dev)
+    if z is None:
+        z = _ZEROS1[dev] = torch.zeros(1, device=dev)
+    return z.view(1)
+
 
 
 def dropout_rng(p_cnn: float, p_enc: float, p_dec: float) -> Optional[Dropout]:
@@ -130,6 +140,7 @@ class ModelForward(torch.autograd.Function):
         targets = targets.contiguous()
         dims = make_dims(cfg, B, Ti, Tt, commands.shape[1])
         _lib.check(lib.gscan_check_dims(dims), "gscan_check_dims")
+        ctx.set_materialize_grads(False)     # no zero-filled gradients for outputs nobody differentiates
         M = dims.G * dims.G
         n_ws = lib.gscan_workspace_floats(dims)
         ws = torch.empty(n_ws, dtype=torch.float32, device=dev)
@@ -156,7 +167,7 @@ class ModelForward(torch.autograd.Function):
         ctx.mask_present = [m is not None for m in masks]
         ctx.param_present = [p is not None for p in params]
         if aux is None:
-            aux = torch.zeros(1, device=dev)
+            aux = _zeros1(dev)
             ctx.mark_non_differentiable(aux)
         return logp, aux
 
@@ -247,10 +258,11 @@ class NLLLoss(torch.autograd.Function):
     def forward(ctx, logp, targets, pad_idx, shift):
         lib = _lib.load()
         _require_cuda(logp, targets)
+        ctx.set_materialize_grads(False)
         logp = logp.contiguous().float()
         targets = targets.contiguous()
         B, T, V = logp.shape
-        out = torch.empty(2, dtype=torch.float32, device=logp.device)
+        out = torch.empty(68, dtype=torch.float32, device=logp.device)   # GSCAN_NLL_OUT_FLOATS: [mean, count | scratch]
         _lib.check(lib.gscan_nll_forward(_ptr(logp), _ptr(targets), B, T, V, int(pad_idx), int(shift), _ptr(out),
                                          _stream(logp.device)), "gscan_nll_forward")
         _call_counts["other"] += 1
@@ -263,6 +275,8 @@ class NLLLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_loss, _d_count):
         lib = _lib.load()
+        if d_loss is None:
+            return None, None, None, None
         targets, out = ctx.saved_tensors
         B, T, V, pad_idx, shift = ctx.meta
         d_loss = d_loss.contiguous().float().reshape(1)

@@ -43,6 +43,7 @@ class FusedTrainer:
         # persistent flat gradient buffer: [gradients in parameters() order | n_tok, n_examples, 0, 0]; the backward
         # pass writes into it (ops.set_flat_grad_target), the data-parallel all-reduce sums all of it at once
         self.flat_grad = torch.zeros(n + dp.COUNT_SLOTS, dtype=torch.float32, device=dev)
+        self._one = torch.ones((), dtype=torch.float32, device=dev)   # d loss / d loss, without a fill kernel per step
         # re-seat every parameter as a view into the flat buffer (identity of the nn.Parameter kept)
         with torch.no_grad():
             for p, view in zip(self._present, self._views(self.flat_param)):
@@ -109,7 +110,7 @@ class FusedTrainer:
             loss = dp.global_loss(nll, aux_mean, self.weight_target_loss)
         ops.set_flat_grad_target(self.flat_grad)
         try:
-            grads = torch.autograd.grad(loss, self._present)
+            grads = torch.autograd.grad(loss, self._present, grad_outputs=self._one)
         finally:
             ops.set_flat_grad_target(None)
         flat_grad = self._flat_gradient(grads)
