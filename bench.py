@@ -433,6 +433,8 @@ def measure_training(wl, steps, warmup, flush, barrier, dist, lib):
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     launches0 = lib.gscan_launch_count()
+    if wl.distributed:
+        wl.trainer.collective_events = []
     barrier()
     for i in range(steps):
         flush.zero_()
@@ -441,9 +443,28 @@ def measure_training(wl, steps, warmup, flush, barrier, dist, lib):
         ends[i].record()
     barrier()
     launches = lib.gscan_launch_count() - launches0
-    total_ms = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], dtype=torch.float64, device=wl.dev)
+    per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(per_step)], dtype=torch.float64, device=wl.dev)
+    wl.dp_timeline = None
     if wl.distributed:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        # Where the step of rank r spends its time around the one collective: [own step, stream time inside the
+        # all-reduce].  A rank that arrives early waits inside the collective for the last one, so the SMALLEST
+        # all-reduce time over ranks is the cost of the collective itself and the spread is rank skew.
+        evs = wl.trainer.collective_events
+        wl.trainer.collective_events = None
+        mine = torch.tensor([sum(per_step) / steps, sum(a.elapsed_time(b) for a, b in evs) / max(1, len(evs))],
+                            dtype=torch.float64, device=wl.dev)
+        allr = [torch.zeros_like(mine) for _ in range(wl.world)]
+        dist.all_gather(allr, mine)
+        rows = [[round(float(x), 4) for x in t.tolist()] for t in allr]
+        wl.dp_timeline = {"per_rank_ms": {"step": [r[0] for r in rows], "in_allreduce": [r[1] for r in rows]},
+                          "collective_ms": min(r[1] for r in rows), "max_wait_in_collective_ms": max(r[1] for r in rows),
+                          "compute_ms_slowest_rank": max(r[0] - r[1] for r in rows),
+                          "compute_ms_fastest_rank": min(r[0] - r[1] for r in rows),
+                          "note": "one NCCL all-reduce of the flat buffer (gradients + loss normalisers) per step; "
+                                  "collective_ms = smallest stream time inside it over the ranks (the rank that arrives last "
+                                  "waits for nobody); step(N) - step(1) = collective + skew of the slowest rank's compute"}
     return total_ms.item() / steps, int(launches)
 
 
@@ -698,6 +719,7 @@ def main():
             "reference_gpu_eager": reference_gpu,
             "decode": decode,
             "extra_workloads": extra,
+            "dp_timeline": getattr(wl, "dp_timeline", None),
         }
         print(json.dumps(line), file=json_out, flush=True)
     if distributed:

@@ -27,6 +27,7 @@ class FusedTrainer:
         self.distributed = distributed
         self.group = process_group
         self.step_count = 0
+        self.collective_events = None    # set to a list to have (before, after) CUDA events of the gradient all-reduce appended
         self.params = list(model.parameters())
         plist = model._param_list()
         self._shapes = [None if p is None else tuple(p.shape) for p in plist]
@@ -118,7 +119,13 @@ class FusedTrainer:
         if self.distributed:
             if flat_grad is not self.flat_grad:
                 flat_grad[n:n + 2].copy_(self.flat_grad[n:n + 2])
+            if self.collective_events is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             dp.allreduce_flat_gradient(flat_grad, self.group)     # the single collective of the step
+            if self.collective_events is not None:
+                ev[1].record()
+                self.collective_events.append(ev)
             denom = flat_grad[n:n + 1]                            # global token count, still on the device
         lr = self.current_lr()
         self.step_count += 1
