@@ -29,6 +29,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// maximum over the warp in ONE instruction (redux.sync.max.f32 -> CREDUX.MAX.F32, new on sm_100a) instead of five
+// shuffle + max pairs; -inf is handled, the softmaxes never see NaN
+__device__ __forceinline__ float warp_max_redux(float v) {
+  float m;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(v));
+  return m;
+}
+
 // tanh / sigmoid with ~1e-7 absolute error: one ex2.approx + one rcp.approx on the SFU instead
 // of libm's ~25-instruction tanhf.  The attention scores need (Ti + G*G) * H tanh per example per
 // decoder step, which makes the SFU the second-busiest pipe of the recurrent sweep.

@@ -830,7 +830,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         for (int r = 0; r < kC; ++r) s += xT_s[(r * kNB + n) * Ti + lane];
         if (lane >= len_s[n]) s = -INFINITY;
       }
-      const float mx = warp_max(s);
+      const float mx = warp_max_redux(s);
       const float e = (lane < Ti) ? __expf(s - mx) : 0.f;
       const float sum = warp_sum(e);
       const float a = e * (1.0f / sum);
@@ -850,16 +850,24 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     // ---- everything linear in c_T through P_j = W K^T_j: q' slice (X3), gate contributions, c_T slice ----
-    if (tid < kNB * (QB + 5)) {
-      const int n = tid / (QB + 5), q = tid - n * (QB + 5);
+    // Two lanes per (example, float4 of outputs): even / odd command positions, combined with one shuffle each (the serial
+    // sum over Ti positions was the longest dependent chain of the phase: 1,500 cycles per step in the timeline)
+    if (tid < 2 * kNB * (QB + 5)) {
+      const int idx = tid >> 1, u = tid & 1;
+      const int n = idx / (QB + 5), q = idx - n * (QB + 5);
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* src = (q < QB) ? P_s + (size_t)n * Ti * RBl + 4 * q : KT_s + (size_t)n * Ti * kHS + 4 * (q - QB);
       const int stride = (q < QB) ? RBl : kHS;
-      for (int j = 0; j < Ti; ++j) {
+#pragma unroll 4
+      for (int j = u; j < Ti; j += 2) {
         const float a = al_s[n * Ti + j];
         const float4 v = lds4(src + j * stride);
         o.x = fmaf(a, v.x, o.x); o.y = fmaf(a, v.y, o.y); o.z = fmaf(a, v.z, o.z); o.w = fmaf(a, v.w, o.w);
       }
+      o.x += __shfl_xor_sync(0xffffffffu, o.x, 1);
+      o.y += __shfl_xor_sync(0xffffffffu, o.y, 1);
+      o.z += __shfl_xor_sync(0xffffffffu, o.z, 1);
+      o.w += __shfl_xor_sync(0xffffffffu, o.w, 1);
       if (COND && q < 5) {
         const float4 chv = lds4(ch_s + n * kHS + 4 * q);
         const float4 bcv = lds4(bc_s + 4 * q);
@@ -869,20 +877,25 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         qq.z = act_tanh(chv.z + o.z + bcv.z);
         qq.w = act_tanh(chv.w + o.w + bcv.w);
         const uint32_t off = (uint32_t)(L.qpfull + n * kXS + S0 + 4 * q) * 4u;
+        // lane 0 of the pair -> CTAs 0, 1, 2; lane 1 -> CTAs 3, 4
 #pragma unroll
-        for (int d = 0; d < kC; ++d) {
-          const uint32_t w = RB(d);
-          st_async_f32x4(w + off, qq, w + boff + 8u * 1);
+        for (int d = 0; d < 3; ++d) {
+          if (u == 0 || d < 2) {
+            const uint32_t w = RB(u == 0 ? d : 3 + d);
+            st_async_f32x4(w + off, qq, w + boff + 8u * 1);
+          }
         }
-      } else if (q < QB) {
-        float4* gp = reinterpret_cast<float4*>(g_s + n * kGS + 4 * q - (COND ? kHS : 0));
-        float4 gv = *gp;
-        gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
-        *gp = gv;
-      } else if (GREEDY) {
-        *reinterpret_cast<float4*>(u_s + n * 3 * kHS + kHS + 4 * (q - QB)) = o;
-      } else {
-        *reinterpret_cast<float4*>(cT_s + n * kHS + 4 * (q - QB)) = o;
+      } else if (u == 0) {
+        if (q < QB) {
+          float4* gp = reinterpret_cast<float4*>(g_s + n * kGS + 4 * q - (COND ? kHS : 0));
+          float4 gv = *gp;
+          gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+          *gp = gv;
+        } else if (GREEDY) {
+          *reinterpret_cast<float4*>(u_s + n * 3 * kHS + kHS + 4 * (q - QB)) = o;
+        } else {
+          *reinterpret_cast<float4*>(cT_s + n * kHS + 4 * (q - QB)) = o;
+        }
       }
     }
     GSCAN3_STAMP(6);
@@ -928,7 +941,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
 #pragma unroll
         for (int r = 0; r < kC; ++r) s1 += xV_s[(r * kNB + n) * kM + 32 + lane];
       }
-      const float mx = warp_max(fmaxf(s0, s1));
+      const float mx = warp_max_redux(fmaxf(s0, s1));
       const float e0 = __expf(s0 - mx), e1 = (lane < kM - 32) ? __expf(s1 - mx) : 0.f;
       const float inv = 1.0f / warp_sum(e0 + e1);
       const float w0 = e0 * inv, w1 = e1 * inv;
