@@ -33,7 +33,7 @@ constexpr int kOutRow = 120;    // [gates i f g o: 80 | h_t: 20 | c_t: 20] per e
 constexpr int kIoWarp0 = 14, kIoThreads = 64;   // backward sweep: warps 14, 15 move the per-step global traffic
 constexpr int kIoWarp0F = 8, kIoThreadsF = 256; // forward sweep: warps 8-15 (stage D / C owners and the spare warp, idle
                                                 // outside their own stage) - one or two 16-byte accesses per thread and site
-constexpr int kTlStamps = 24;   // phase stamps per step of the instrumented (TL) instantiations: 0-15 phases, 16+ sub-phases
+constexpr int kTlStamps = 32;   // phase stamps per step of the instrumented (TL) instantiations: 0-15 phases, 16+ sub-phases
 
 // ---- PTX helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -830,9 +830,12 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
         for (int r = 0; r < kC; ++r) s += xT_s[(r * kNB + n) * Ti + lane];
         if (lane >= len_s[n]) s = -INFINITY;
       }
+      GSCAN3_STAMP(24);
       const float mx = warp_max_redux(s);
+      GSCAN3_STAMP(25);
       const float e = (lane < Ti) ? __expf(s - mx) : 0.f;
       const float sum = warp_sum(e);
+      GSCAN3_STAMP(26);
       const float a = e * (1.0f / sum);
       if (lane < Ti) {
         al_s[n * Ti + lane] = a;
@@ -850,53 +853,83 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     // ---- everything linear in c_T through P_j = W K^T_j: q' slice (X3), gate contributions, c_T slice ----
-    // Two lanes per (example, float4 of outputs): even / odd command positions, combined with one shuffle each (the serial
-    // sum over Ti positions was the longest dependent chain of the phase: 1,500 cycles per step in the timeline)
-    if (tid < 2 * kNB * (QB + 5)) {
-      const int idx = tid >> 1, u = tid & 1;
-      const int n = idx / (QB + 5), q = idx - n * (QB + 5);
+    // Only q' (5 float4 per example: 40 outputs) is on the critical path of the step - it feeds the X3 exchange and
+    // stage C; the gate contributions and the c_T slice (25 float4 per example) are first read by the cell / the I/O
+    // warps, two block barriers later.  The 40 critical outputs get four lanes each (positions j = u, u + 4, ...:
+    // three terms at Ti = 10 instead of ten), two shuffle rounds, and the five sends spread over the four lanes; the 200
+    // others run one thread each on warps 5-11, off the critical path.  (One thread per output for all 240, as in
+    // round 1, made this phase ~1,700 cycles of a 12,000-cycle step in the per-warp timeline.  Putting the critical
+    // group on the warps the scheduler favours, 11-15, measured slower: 0.741 vs 0.721 ms.)
+    if (COND && tid < 4 * kNB * 5) {
+      const int idx = tid >> 2, u = tid & 3;
+      const int n = idx / 5, q = idx - n * 5;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = P_s + (size_t)n * Ti * RBl + 4 * q;
+#pragma unroll 4
+      for (int j = u; j < Ti; j += 4) {
+        const float a = al_s[n * Ti + j];
+        const float4 v = lds4(src + j * RBl);
+        o.x = fmaf(a, v.x, o.x); o.y = fmaf(a, v.y, o.y); o.z = fmaf(a, v.z, o.z); o.w = fmaf(a, v.w, o.w);
+      }
+#pragma unroll
+      for (int sh = 1; sh <= 2; sh <<= 1) {
+        o.x += __shfl_xor_sync(0xffffffffu, o.x, sh);
+        o.y += __shfl_xor_sync(0xffffffffu, o.y, sh);
+        o.z += __shfl_xor_sync(0xffffffffu, o.z, sh);
+        o.w += __shfl_xor_sync(0xffffffffu, o.w, sh);
+      }
+      GSCAN3_STAMP(23);
+      const float4 chv = lds4(ch_s + n * kHS + 4 * q);
+      const float4 bcv = lds4(bc_s + 4 * q);
+      float4 qq;
+      qq.x = act_tanh(chv.x + o.x + bcv.x);
+      qq.y = act_tanh(chv.y + o.y + bcv.y);
+      qq.z = act_tanh(chv.z + o.z + bcv.z);
+      qq.w = act_tanh(chv.w + o.w + bcv.w);
+      const uint32_t off = (uint32_t)(L.qpfull + n * kXS + S0 + 4 * q) * 4u;
+      const uint32_t wu = RB_U;   // lane u of the group -> CTA u, lane 0 also -> CTA 4
+      st_async_f32x4(wu + off, qq, wu + boff + 8u * 1);
+      if (u == 0) {
+        const uint32_t w4 = RB_4;
+        st_async_f32x4(w4 + off, qq, w4 + boff + 8u * 1);
+      }
+    } else if (tid >= 4 * kNB * 5 && tid < 4 * kNB * 5 + kNB * QB) {
+      // (without conditional attention QB = 20: the gate contributions and c_T only, nothing critical)
+      const int idx = tid - 4 * kNB * 5;
+      const int n = idx / QB, q = (COND ? 5 : 0) + idx - n * QB;   // q in [5, 30) with COND, [0, 20) + c_T below without
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       const float* src = (q < QB) ? P_s + (size_t)n * Ti * RBl + 4 * q : KT_s + (size_t)n * Ti * kHS + 4 * (q - QB);
       const int stride = (q < QB) ? RBl : kHS;
-#pragma unroll 4
-      for (int j = u; j < Ti; j += 2) {
+#pragma unroll 2
+      for (int j = 0; j < Ti; ++j) {
         const float a = al_s[n * Ti + j];
         const float4 v = lds4(src + j * stride);
         o.x = fmaf(a, v.x, o.x); o.y = fmaf(a, v.y, o.y); o.z = fmaf(a, v.z, o.z); o.w = fmaf(a, v.w, o.w);
       }
-      o.x += __shfl_xor_sync(0xffffffffu, o.x, 1);
-      o.y += __shfl_xor_sync(0xffffffffu, o.y, 1);
-      o.z += __shfl_xor_sync(0xffffffffu, o.z, 1);
-      o.w += __shfl_xor_sync(0xffffffffu, o.w, 1);
-      if (COND && q < 5) {
-        const float4 chv = lds4(ch_s + n * kHS + 4 * q);
-        const float4 bcv = lds4(bc_s + 4 * q);
-        float4 qq;
-        qq.x = act_tanh(chv.x + o.x + bcv.x);
-        qq.y = act_tanh(chv.y + o.y + bcv.y);
-        qq.z = act_tanh(chv.z + o.z + bcv.z);
-        qq.w = act_tanh(chv.w + o.w + bcv.w);
-        const uint32_t off = (uint32_t)(L.qpfull + n * kXS + S0 + 4 * q) * 4u;
-        // lane 0 of the pair -> CTAs 0, 1, 2; lane 1 -> CTAs 3, 4
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          if (u == 0 || d < 2) {
-            const uint32_t w = RB(u == 0 ? d : 3 + d);
-            st_async_f32x4(w + off, qq, w + boff + 8u * 1);
-          }
-        }
-      } else if (u == 0) {
-        if (q < QB) {
-          float4* gp = reinterpret_cast<float4*>(g_s + n * kGS + 4 * q - (COND ? kHS : 0));
-          float4 gv = *gp;
-          gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
-          *gp = gv;
-        } else if (GREEDY) {
-          *reinterpret_cast<float4*>(u_s + n * 3 * kHS + kHS + 4 * (q - QB)) = o;
-        } else {
-          *reinterpret_cast<float4*>(cT_s + n * kHS + 4 * (q - QB)) = o;
-        }
+      if (q < QB) {
+        float4* gp = reinterpret_cast<float4*>(g_s + n * kGS + 4 * q - (COND ? kHS : 0));
+        float4 gv = *gp;
+        gv.x += o.x; gv.y += o.y; gv.z += o.z; gv.w += o.w;
+        *gp = gv;
+      } else if (GREEDY) {
+        *reinterpret_cast<float4*>(u_s + n * 3 * kHS + kHS + 4 * (q - QB)) = o;
+      } else {
+        *reinterpret_cast<float4*>(cT_s + n * kHS + 4 * (q - QB)) = o;
       }
+    }
+    if (!COND && tid >= 4 * kNB * 5 + kNB * QB && tid < 4 * kNB * 5 + kNB * QB + kNB * 5) {
+      // c_T slice without conditional attention (the five float4 per example that COND covers as q in [25, 30) above)
+      const int idx = tid - (4 * kNB * 5 + kNB * QB);
+      const int n = idx / 5, q = idx - n * 5;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float* src = KT_s + (size_t)n * Ti * kHS + 4 * q;
+      for (int j = 0; j < Ti; ++j) {
+        const float a = al_s[n * Ti + j];
+        const float4 v = lds4(src + j * kHS);
+        o.x = fmaf(a, v.x, o.x); o.y = fmaf(a, v.y, o.y); o.z = fmaf(a, v.z, o.z); o.w = fmaf(a, v.w, o.w);
+      }
+      if (GREEDY) *reinterpret_cast<float4*>(u_s + n * 3 * kHS + kHS + 4 * q) = o;
+      else *reinterpret_cast<float4*>(cT_s + n * kHS + 4 * q) = o;
     }
     GSCAN3_STAMP(6);
     // ---- stage C: visual query slice ---------------------------------------------------------------------

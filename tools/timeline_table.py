@@ -1,9 +1,9 @@
 """Per-warp table of the phase stamps of the instrumented sweeps (GSCAN_TIMELINE=<prefix> dumps <prefix>.fwd.bin /
-<prefix>.bwd.bin: [T][24 stamps][16 warps] clock64 values of CTA 0, lane 0 of every warp).  Rows = stamps, columns =
+<prefix>.bwd.bin: [T][32 stamps][16 warps] clock64 values of CTA 0, lane 0 of every warp).  Rows = stamps, columns =
 warps; entries = average cycles after the step's first stamp.  Usage: timeline_table.py file.bin"""
 import sys
 import numpy as np
-NS = 24
+NS = 32
 h = np.fromfile(sys.argv[1], dtype=np.int64)
 T = h.size // (NS * 16)
 h = h.reshape(T, NS, 16).astype(np.float64)
