@@ -371,12 +371,16 @@ __device__ __forceinline__ void partial_scores(const float* __restrict__ q_s, co
 template <int NKEYS_CT, int LANES>
 __device__ __forceinline__ void partial_scores_vec(const float* __restrict__ q_s, const float* __restrict__ K_s,
                                                    const float* __restrict__ v_s, int nkeys, int xoff_floats, int rank,
-                                                   uint32_t rb_k, uint32_t rb_4, uint32_t bar_off) {
-  // rb_k: shared-memory window of CTA (lane & 3) for LANES = 1, of CTA min(lane & 7, 4) for LANES = 2; rb_4: of CTA 4
+                                                   uint32_t rb_k, uint32_t rb_4, uint32_t bar_off, int w0 = 0,
+                                                   int nw = kThreads / 32) {
+  // rb_k: shared-memory window of CTA (lane & 3) for LANES = 1, of CTA min(lane & 7, 4) for LANES = 2; rb_4: of CTA 4;
+  // the items are spread over the warps w0 .. w0 + nw - 1 (whole warps: the shuffles below use the full mask)
   static_assert(LANES == 1 || LANES == 2, "20 hidden units per CTA: 1 x 20 or 2 x 10");
   const int N = NKEYS_CT > 0 ? NKEYS_CT : nkeys;
   const int total = kNB * N * LANES;
-  for (int base = (threadIdx.x >> 5) * 32; base < total; base += kThreads) {
+  const int wrel = (int)(threadIdx.x >> 5) - w0;
+  if (wrel < 0 || wrel >= nw) return;
+  for (int base = wrel * 32; base < total; base += nw * 32) {
     const int item = base + (threadIdx.x & 31);
     const int pair = item / LANES, u = item - pair * LANES;
     float s = 0.f;
@@ -550,7 +554,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     };
     auto rowC = [&](int lr) -> const float* { return lr < kHS ? p.W_qV + (size_t)(S0 + lr) * kH : nullptr; };
     if (roleA) {
-      lr0 = 16 * warp + fg;
+      // tile 0 (the q_T rows, which the text scores wait for) on warp 7: the scheduler favours the higher warp index
+      lr0 = 16 * (7 - warp) + fg;
       r0 = rowA(lr0);
       r1 = rowA(lr0 + 8);
     } else if (roleD) {
@@ -806,7 +811,16 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       GSCAN3_STAMP(17);
     }
     GSCAN3_STAMP(18);
-    __syncthreads();
+    // Only q_T (tiles 0 and 1: warps 7 and 6) is needed now; W_c h is first read after the text softmax, the gate rows by
+    // the cell.  Training sweep with conditional attention: no block barrier here - warps 6 and 7 hand q_T over to warps
+    // 8-12 (named barrier 2), which form the text scores and start the X1 exchange while the other stage-A tiles finish.
+    constexpr bool kEarlyText = COND && !GREEDY;
+    if (kEarlyText) {
+      if (warp == 6 || warp == 7) asm volatile("bar.arrive 2, 224;" ::: "memory");
+      else if (warp >= 8 && warp < 13) asm volatile("bar.sync 2, 224;" ::: "memory");
+    } else {
+      __syncthreads();
+    }
     GSCAN3_STAMP(2);
     if (!GREEDY) {
       // I/O warps: q_T of this step (and q_V, q' = h_{t-1} without conditional attention)
@@ -817,7 +831,8 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     // ---- textual attention: partial scores over the local slice, summed over ranks (X1) ---------------
-    partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, RB_8, RB_4, boff + 0u);
+    if (kEarlyText) partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, RB_8, RB_4, boff + 0u, 8, 5);
+    else partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, RB_8, RB_4, boff + 0u);
     GSCAN3_STAMP(3);
     mbar_wait(bar0 + 8u * 0, par);
     GSCAN3_STAMP(4);
