@@ -188,7 +188,7 @@ __host__ __device__ inline FwdSmem fwd_smem(int Ti, int cond, int greedy_V = 0) 
   s.hfull = take(kNB * kXS);
   s.qpfull = take(kNB * kXS);
   s.cvfull = take(kNB * kXS);
-  s.xT = take(kC * kNB * Ti);
+  s.xT = take(kC * kNB * kMaxTi);   // partial text scores of every rank, kMaxTi slots per example
   s.xV = take(kC * kNB * kM);
   s.P = take(kNB * Ti * RBl);
   s.KT = take(kNB * Ti * kHS);
@@ -479,6 +479,44 @@ __device__ __forceinline__ void partial_scores_q4(const float* __restrict__ q_s,
   }
 }
 
+// Text scores, one example per warp (warps w0 .. w0 + 7): lane = 2 * key + half, ten hidden units per lane.  No index
+// arithmetic beyond shifts (the generic routine above spends ~270 warp-instructions per 32 items, a quarter of them on
+// the division by the run-time Ti and on loop control), key slots >= Ti idle.  The partial scores travel in a layout
+// padded to kMaxTi keys per example, four keys per 16-byte st.async: lanes 0..4 of each group of eight -> CTA 0..4.
+// rb_8 = window of CTA min(lane & 7, 4).
+__device__ __forceinline__ void text_scores_warp(const float* __restrict__ q_s, const float* __restrict__ K_s,
+                                                 const float* __restrict__ v_s, int Ti, int xoff_floats, int rank,
+                                                 uint32_t rb_8, uint32_t bar_off, int w0) {
+  const int n = (int)(threadIdx.x >> 5) - w0, lane = threadIdx.x & 31;
+  if (n < 0 || n >= kNB) return;
+  const int j = lane >> 1, u = lane & 1;
+  float s = 0.f;
+  if (j < Ti) {
+    const float2* kp = reinterpret_cast<const float2*>(K_s + (n * Ti + j) * kHS + 10 * u);
+    const float2* qp = reinterpret_cast<const float2*>(q_s + n * kHS + 10 * u);
+    const float2* vp = reinterpret_cast<const float2*>(v_s + 10 * u);
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float2 k = kp[i], q = qp[i], v = vp[i];
+      s = fmaf(v.x, act_tanh(q.x + k.x), s);
+      s1 = fmaf(v.y, act_tanh(q.y + k.y), s1);
+    }
+    s += s1;
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  const int g0 = lane & ~7, k = lane & 7;
+  float4 o;
+  o.x = __shfl_sync(0xffffffffu, s, g0);
+  o.y = __shfl_sync(0xffffffffu, s, g0 + 2);
+  o.z = __shfl_sync(0xffffffffu, s, g0 + 4);
+  o.w = __shfl_sync(0xffffffffu, s, g0 + 6);
+  if ((g0 >> 1) < Ti && k < kC) {
+    const uint32_t off = (uint32_t)(xoff_floats + (rank * kNB + n) * kMaxTi + (g0 >> 1)) * 4u;
+    st_async_f32x4(rb_8 + off, o, rb_8 + bar_off);
+  }
+}
+
 template <bool COND, bool GREEDY, bool TL = false>
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fwd_v3_kernel(DecFwd3P p) {
   extern __shared__ __align__(16) float smem[];
@@ -719,7 +757,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
   __syncthreads();
   cluster_barrier();
 
-  const uint32_t bytes_xT = (uint32_t)(kC * kNB * Ti * 4), bytes_vec = (uint32_t)(kNB * kH * 4),
+  const uint32_t bytes_xT = (uint32_t)(kC * kNB * ((Ti + 3) / 4) * 16), bytes_vec = (uint32_t)(kNB * kH * 4),
                  bytes_xV = (uint32_t)(kC * kNB * kM * 4);
   bool finished_early = false;   // greedy: every sequence of this cluster ended before the step limit
   // greedy (predict.py:106-117), run by warp 15: wait for the logit partial sums of step s (X7), pick the token of each
@@ -813,11 +851,11 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(18);
     // Only q_T (tiles 0 and 1: warps 7 and 6) is needed now; W_c h is first read after the text softmax, the gate rows by
     // the cell.  Training sweep with conditional attention: no block barrier here - warps 6 and 7 hand q_T over to warps
-    // 8-12 (named barrier 2), which form the text scores and start the X1 exchange while the other stage-A tiles finish.
+    // 8-15 (named barrier 2), which form the text scores and start the X1 exchange while the other stage-A tiles finish.
     constexpr bool kEarlyText = COND && !GREEDY;
     if (kEarlyText) {
-      if (warp == 6 || warp == 7) asm volatile("bar.arrive 2, 224;" ::: "memory");
-      else if (warp >= 8 && warp < 13) asm volatile("bar.sync 2, 224;" ::: "memory");
+      if (warp == 6 || warp == 7) asm volatile("bar.arrive 2, 320;" ::: "memory");
+      else if (warp >= 8) asm volatile("bar.sync 2, 320;" ::: "memory");
     } else {
       __syncthreads();
     }
@@ -831,8 +869,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     // ---- textual attention: partial scores over the local slice, summed over ranks (X1) ---------------
-    if (kEarlyText) partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, RB_8, RB_4, boff + 0u, 8, 5);
-    else partial_scores_vec<0, 2>(qT_s, KT_s, vT_s, Ti, L.xT, rank, RB_8, RB_4, boff + 0u);
+    text_scores_warp(qT_s, KT_s, vT_s, Ti, L.xT, rank, RB_8, boff + 0u, kEarlyText ? 8 : 0);
     GSCAN3_STAMP(3);
     mbar_wait(bar0 + 8u * 0, par);
     GSCAN3_STAMP(4);
@@ -842,7 +879,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       if (lane < Ti) {
         s = 0.f;
 #pragma unroll
-        for (int r = 0; r < kC; ++r) s += xT_s[(r * kNB + n) * Ti + lane];
+        for (int r = 0; r < kC; ++r) s += xT_s[(r * kNB + n) * kMaxTi + lane];
         if (lane >= len_s[n]) s = -INFINITY;
       }
       GSCAN3_STAMP(24);
