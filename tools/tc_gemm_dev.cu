@@ -6,6 +6,7 @@
 #include <random>
 #include <cmath>
 #include <cstring>
+#include "../include/gscan_b200.h"
 #include "../multimodal_seq2seq_gscan_b200/csrc/gemm.cuh"
 #include "../multimodal_seq2seq_gscan_b200/csrc/gemm_tc.cuh"
 
