@@ -96,6 +96,7 @@ void chain_report(const char* title) {
 struct SideStreams {
   cudaStream_t s[3] = {nullptr, nullptr, nullptr};   // [0], [1]: high priority chains; [2]: shadow work, lowest priority
   cudaEvent_t fork_ev[3] = {nullptr, nullptr, nullptr}, join_ev[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};   // forward pass: [0] command encoder done, [1] Wcomb, [2] encoder about to start
   bool ok = false;
 };
 SideStreams* side_streams() {
@@ -113,6 +114,8 @@ SideStreams* side_streams() {
       if (cudaEventCreateWithFlags(&S.fork_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&S.join_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
+    for (int i = 0; i < 3; ++i)
+      if (cudaEventCreateWithFlags(&S.aux_ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     S.ok = true;
   }
   return &S;
@@ -142,6 +145,7 @@ struct Layout {
   size_t Wt_cnn, feat, KV, enc_x, xg[2], enc_h[2], enc_c[2], enc_g[2], enc_out, h_enc, KT, h0;
   size_t WA_t, WB_t, WC_t, WD_t, WhhE_t[2];
   size_t WA2, WC2, WD2, PT;   // cluster-resident decoder sweep (decoder_cluster.cuh)
+  size_t Wcomb;               // [RB][H] = [W_c[:, H:2H] ; W_ih[:, H:2H]] . W_kT: P straight from the encoder outputs
   size_t U, Xe, Cs, gates, alpha, beta, Qp, qT, qV, beta_sum, aux_logp, pre, logp;
   size_t tag;                  // which decoder sweep the forward call ran (checked by the v3 backward kernel)
   // backward scratch
@@ -179,6 +183,7 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
   L.WC2 = L.take(H * H);
   L.WD2 = L.take(H * 4 * H);
   L.PT = L.take(Ti * B * (size_t)L.RB);
+  L.Wcomb = L.take((size_t)L.RB * H);
   L.U = L.take((Tt + 1) * B * 4 * H);
   L.Xe = L.take(Tt * B * 4 * H);
   L.Cs = L.take((Tt + 1) * B * H);
@@ -401,6 +406,10 @@ int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* sit
       const_cast<float*>(P[GSCAN_P_CONV3_W]), Wt, 1);
   GSCAN_CHECK_LAUNCH();
   size_t smem = (size_t)cs.M() * cs.C * 8;
+  // GSCAN_CNN_SMEM_KB: ask for more shared memory than the kernel uses, which bounds its CTAs per SM (8 of them fill
+  // every thread slot of an SM for ~35 us each, and the small kernels of the encoder chain queue behind them)
+  static const int pad_kb = env_int("GSCAN_CNN_SMEM_KB", 0);
+  if (pad_kb > 0 && smem < (size_t)pad_kb * 1024) smem = (size_t)pad_kb * 1024;
   if (smem > 48 * 1024) TRY(set_smem(cnn_forward_kernel, smem));
   const int ysplit = max(1, min(8, ceil_div(cs.M() * cs.D(), 3 * 256)));   // ~3 outputs per thread
   cnn_forward_kernel<<<dim3(d.B, ysplit), 256, smem, st>>>(cs, situations, Wt, P[GSCAN_P_CONV1_B], P[GSCAN_P_CONV2_B],
@@ -415,16 +424,36 @@ int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* sit
 int run_encoder_side(const gscan_dims& d, const float* const* P, const long long* commands, const int* cmd_len,
                      const float* situations, DropSrc drop_cnn, DropSrc drop_enc, float* ws,
                      const Layout& L, bool need_keys, cudaStream_t st, cudaStream_t cnn_stream = nullptr,
-                     bool cnn_stream_given = false) {
+                     bool cnn_stream_given = false, cudaEvent_t enc_done = nullptr) {
   const int B = d.B, Ti = d.Ti, M = d.G * d.G, D = 3 * d.F, H = d.H, E = d.E;
   // the situation CNN (+ visual keys) is independent of the command encoder
   SideStreams* S = cnn_stream_given ? nullptr : side_streams();
   cudaStream_t sc = cnn_stream_given ? cnn_stream : (S ? S->s[0] : st);
   if (S) TRY(fork_side(S, 0, st));
-  TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, sc));
-  chain_mark("cnn", sc);
-  if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, sc));
-  chain_mark("KV", sc);
+  // GSCAN_CNN_AFTER=1: the CNN starts when the encoder's recurrent kernel does (its 1600 CTAs otherwise take every
+  // thread slot of the chip for ~40 us and the small kernels at the head of the encoder chain queue behind them)
+  static const bool cnn_after = env_int("GSCAN_CNN_AFTER", 0) != 0;
+  SideStreams* SE = side_streams();
+  const bool defer_cnn = cnn_after && SE && sc != st;
+  auto cnn_chain = [&]() -> int {
+    TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, sc));
+    chain_mark("cnn", sc);
+    if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, sc));
+    chain_mark("KV", sc);
+    return 0;
+  };
+  if (!defer_cnn) TRY(cnn_chain());
+  // weight packing and the zero fills first: the chip is still empty then; behind the input GEMMs they queued for
+  // SM slots behind the CNN's CTAs (a 2 us fill took 15 us: tools/step_trace.py)
+  {
+    PackTable tab;
+    tab.n = 2;
+    tab.d[0] = PackDesc{P[GSCAN_P_ENC_WHH], H, 0, ws + L.WhhE_t[0], 4 * H, 0, 4 * H, H};
+    tab.d[1] = PackDesc{P[GSCAN_P_ENC_WHH_R], H, 0, ws + L.WhhE_t[1], 4 * H, 0, 4 * H, H};
+    TRY(launch_pack(tab, st));
+  }
+  TRYCUDA(cudaMemsetAsync(ws + L.enc_out, 0, sizeof(float) * (size_t)Ti * B * H, st));
+  TRYCUDA(cudaMemsetAsync(ws + L.h_enc, 0, sizeof(float) * (size_t)B * H, st));
   // command embeddings and their input-gate pre-activations for both directions
   {
     long n = (long)B * Ti * E;
@@ -436,15 +465,6 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
              P[GSCAN_P_ENC_BHH], 0, st));
   TRY(linear(ws + L.enc_x, E, P[GSCAN_P_ENC_WIH_R], E, ws + L.xg[1], 4 * H, B * Ti, 4 * H, E, P[GSCAN_P_ENC_BIH_R],
              P[GSCAN_P_ENC_BHH_R], 0, st));
-  {
-    PackTable tab;
-    tab.n = 2;
-    tab.d[0] = PackDesc{P[GSCAN_P_ENC_WHH], H, 0, ws + L.WhhE_t[0], 4 * H, 0, 4 * H, H};
-    tab.d[1] = PackDesc{P[GSCAN_P_ENC_WHH_R], H, 0, ws + L.WhhE_t[1], 4 * H, 0, 4 * H, H};
-    TRY(launch_pack(tab, st));
-  }
-  TRYCUDA(cudaMemsetAsync(ws + L.enc_out, 0, sizeof(float) * (size_t)Ti * B * H, st));
-  TRYCUDA(cudaMemsetAsync(ws + L.h_enc, 0, sizeof(float) * (size_t)B * H, st));
   EncP ep{};
   ep.B = B; ep.Ti = Ti; ep.H = H;
   for (int i = 0; i < 2; ++i) {
@@ -457,11 +477,19 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
   ep.len = cmd_len;
   ep.enc_out = ws + L.enc_out;
   ep.h_enc = ws + L.h_enc;
+  if (defer_cnn) {
+    TRYCUDA(cudaEventRecord(SE->aux_ev[2], st));
+    TRYCUDA(cudaStreamWaitEvent(sc, SE->aux_ev[2], 0));
+  }
   TRY(launch_enc(d, ep, false, st));
   chain_mark("enc_fwd", st);
+  if (defer_cnn) TRY(cnn_chain());
+  // with `enc_done` the caller runs what else hangs off the encoder outputs (initial decoder state, P table) on other
+  // streams, beside the textual keys
+  if (enc_done) TRYCUDA(cudaEventRecord(enc_done, st));
   if (need_keys) {
     TRY(linear(ws + L.enc_out, H, P[GSCAN_P_TXT_KEY_W], H, ws + L.KT, H, Ti * B, H, H, nullptr, nullptr, 0, st));
-    TRY(linear(ws + L.h_enc, H, P[GSCAN_P_E2D_W], H, ws + L.h0, H, B, H, H, P[GSCAN_P_E2D_B], nullptr, 1, st));
+    if (!enc_done) TRY(linear(ws + L.h_enc, H, P[GSCAN_P_E2D_W], H, ws + L.h0, H, B, H, H, P[GSCAN_P_E2D_B], nullptr, 1, st));
   }
   if (S) TRY(join_side(S, 0, st));
   return 0;
@@ -691,6 +719,19 @@ int compute_PT(const gscan_dims& d, const float* const* P, const float* KT, floa
   return 0;
 }
 
+// The same table without waiting for the keys: K^T = enc_out . W_kT^T, so P = enc_out . Wcomb^T with
+// Wcomb = [W_c[:, H:2H] ; W_ih[:, H:2H]] . W_kT  ([RB x H], weights only: computed off the critical chain)
+int compute_Wcomb(const gscan_dims& d, const float* const* P, float* Wcomb, cudaStream_t st) {
+  const int H = d.H;
+  const int cH = d.conditional_attention ? H : 0;
+  if (cH) TRY(matmul_nn(P[GSCAN_P_COND_W] + H, 2 * H, P[GSCAN_P_TXT_KEY_W], H, Wcomb, H, H, H, H, 0, st));
+  TRY(matmul_nn(P[GSCAN_P_DEC_WIH] + H, 3 * H, P[GSCAN_P_TXT_KEY_W], H, Wcomb + (size_t)cH * H, H, 4 * H, H, H, 0, st));
+  return 0;
+}
+int compute_PT_direct(const gscan_dims& d, const float* enc_out, const float* Wcomb, float* PT, int RB, cudaStream_t st) {
+  return linear(enc_out, d.H, Wcomb, d.H, PT, RB, d.Ti * d.B, RB, d.H, nullptr, nullptr, 0, st);
+}
+
 // stamps: [T][16 stamps][16 warps] of CTA 0.  Prints, per stamp interval, the average over the steps of the time between
 // consecutive stamps of warp 0 (the round-1 figure), and - what the chain of dependences really looks like - for every
 // stamp the average time at which the EARLIEST and the LATEST warp reached it, relative to the step's start.
@@ -738,14 +779,14 @@ void print_timeline(const char* what, long long* tl, int T, cudaStream_t st) {
 }
 
 int launch_dec_fwd_v3(const gscan_dims& d, const float* const* P, float* ws, const Layout& L, v3::DecFwd3P p,
-                      bool greedy, cudaStream_t st) {
+                      bool greedy, cudaStream_t st, bool pt_ready = false) {
   const int cond = d.conditional_attention ? 1 : 0;
   const v3::FwdSmem sm = v3::fwd_smem(d.Ti, cond, greedy ? d.V : 0);
   const size_t bytes = (size_t)sm.total * sizeof(float);
   if (bytes > kMaxSmemBytes) return GSCAN_E_UNSUPPORTED;
   if (greedy) TRY(cond ? (v3_fwd_prepare<true, true>(bytes)) : (v3_fwd_prepare<false, true>(bytes)));
   else TRY(cond ? (v3_fwd_prepare<true, false>(bytes)) : (v3_fwd_prepare<false, false>(bytes)));
-  TRY(compute_PT(d, P, p.KT, ws + L.PT, L.RB, st));
+  if (!pt_ready) TRY(compute_PT(d, P, p.KT, ws + L.PT, L.RB, st));
   p.PT = ws + L.PT;
   p.W_qT = P[GSCAN_P_TXT_QUERY_W]; p.W_c = P[GSCAN_P_COND_W]; p.W_hh = P[GSCAN_P_DEC_WHH];
   p.W_qV = P[GSCAN_P_VIS_QUERY_W]; p.W_ih = P[GSCAN_P_DEC_WIH];
@@ -991,11 +1032,28 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   // on the caller's 213 us; encoder side on helper streams and prelude on the caller's 183 us.
   SideStreams* S = side_streams();
   cudaStream_t se = S ? S->s[1] : st, sp = S ? S->s[0] : st;
+  // GSCAN_FWD_SCHED: 0 = round-1 schedule (K^T, h0, P one after the other behind the encoder);  1 = the three products
+  // that hang off the encoder outputs run side by side (K^T on the encoder's stream, h0 on the prelude's, P - straight
+  // from enc_out through Wcomb - on the caller's);  2 = and the prelude GEMM waits for the encoder: the encoder's
+  // 100 CTAs and the GEMM's persistent CTAs both need an SM's whole shared memory, and a GEMM that got there first
+  // made the encoder run in two waves (55 us instead of 31: tools/step_trace.py)
+  static const int sched = env_int("GSCAN_FWD_SCHED", 1);
+  const bool par_tail = S && sched >= 1 && v3_shape_ok(*d);
   if (S) {
     TRY(fork_side(S, 1, st));
     TRY(fork_side(S, 0, st));
   }
-  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, se, st, true));
+  if (par_tail) {   // weights only, ahead of the prelude (which has slack)
+    TRY(compute_Wcomb(*d, P, ws + L.Wcomb, sp));
+    TRYCUDA(cudaEventRecord(S->aux_ev[1], sp));
+  }
+  TRY(run_encoder_side(*d, P, cmds, cmd_len, situations, drop_cnn, drop_enc, ws, L, true, se, st, true,
+                       par_tail ? S->aux_ev[0] : nullptr));
+  if (par_tail) {   // the caller's stream: CNN, visual keys, then P as soon as the encoder is done
+    TRYCUDA(cudaStreamWaitEvent(st, S->aux_ev[0], 0));
+    TRYCUDA(cudaStreamWaitEvent(st, S->aux_ev[1], 0));
+    TRY(compute_PT_direct(*d, ws + L.enc_out, ws + L.Wcomb, ws + L.PT, L.RB, st));
+  }
   TRY(pack_decoder_weights(*d, P, ws, L, sp));
   // target embeddings straight into the e-block of U (time-major rows, group 0 reserved for h_{-1})
   {
@@ -1012,9 +1070,15 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   float* U1 = ws + L.U + (size_t)B * 4 * H;
   // input-gate pre-activations of every step at once: Xe = E . W_ih[:, :H]^T + b_ih + b_hh
   {
-    tc::ScopedSmCap cap(S ? cap_prelude() : 0);   // leave SMs to the command encoder running beside it
+    const bool after_enc = par_tail && sched >= 2;
+    if (after_enc) TRYCUDA(cudaStreamWaitEvent(sp, S->aux_ev[0], 0));
+    tc::ScopedSmCap cap(S && !after_enc ? cap_prelude() : 0);   // leave SMs to the command encoder running beside it
     TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, Tt * B, 4 * H, H, P[GSCAN_P_DEC_BIH],
                P[GSCAN_P_DEC_BHH], 0, sp));
+  }
+  if (par_tail) {   // initial decoder state, beside K^T and P
+    TRYCUDA(cudaStreamWaitEvent(sp, S->aux_ev[0], 0));
+    TRY(linear(ws + L.h_enc, H, P[GSCAN_P_E2D_W], H, ws + L.h0, H, B, H, H, P[GSCAN_P_E2D_B], nullptr, 1, sp));
   }
   chain_mark("s0:prelude", sp);
   if (S) TRY(join_side(S, 0, st));
@@ -1057,7 +1121,7 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     p3.KT = p.KT; p3.KV = p.KV; p3.cmd_len = cmd_len; p3.h_init = p.h_init; p3.c_init = p.c_init; p3.Xe = p.Xe;
     p3.U = p.U; p3.Cs = p.Cs; p3.gates = p.gates; p3.alpha = p.alpha; p3.beta = p.beta;
     p3.Qp = p.Qp; p3.qT = p.qT; p3.qV = p.qV; p3.beta_sum = p.beta_sum;
-    int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, false, st);
+    int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, false, st, par_tail);
     if (rc == 0) v3_done = true;
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
   }

@@ -41,13 +41,51 @@ def _param_array(tensors: Sequence[Optional[torch.Tensor]]) -> ParamArray:
     return arr
 
 
+class _PinnedRing:
+    """A few pinned staging buffers of one size, reused round-robin.  A host->device copy from PAGEABLE memory makes the
+    CUDA runtime synchronise the stream before it starts (the host then waits for everything enqueued so far: measured
+    as one host/GPU lock-step per training step, with every launch after it exposed at the host's launch cadence);
+    from pinned memory the copy is truly stream-ordered.  A slot is rewritten only after the copy that last read it
+    has completed (its event), which with several slots is long past."""
+
+    SLOTS = 8
+
+    def __init__(self, n: int):
+        self.bufs = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(self.SLOTS)]
+        self.events = [None] * self.SLOTS
+        self.i = 0
+
+    def stage(self, arr: np.ndarray, device) -> torch.Tensor:
+        k = self.i
+        self.i = (k + 1) % self.SLOTS
+        if self.events[k] is not None:
+            self.events[k].synchronize()
+        np.copyto(self.bufs[k].numpy(), arr, casting="unsafe")
+        out = torch.empty(arr.size, dtype=torch.int32, device=device)
+        out.copy_(self.bufs[k], non_blocking=True)
+        if self.events[k] is None:
+            self.events[k] = torch.cuda.Event()
+        self.events[k].record(torch.cuda.current_stream(device))
+        return out
+
+
+_RINGS: dict = {}
+
+
 def lengths_to_device(lengths, device) -> torch.Tensor:
     """The reference passes lengths as host lists / numpy float64 arrays (gSCAN_dataset.py:198-199);
-    the kernels want int32 on the device.  No sync: the copy is stream-ordered."""
+    the kernels want int32 on the device.  No sync: the copy is stream-ordered (pinned staging ring)."""
     if isinstance(lengths, torch.Tensor):
         return lengths.to(device=device, dtype=torch.int32)
-    arr = np.ascontiguousarray(np.asarray(lengths).astype(np.int32))
-    return torch.from_numpy(arr).to(device, non_blocking=True)
+    arr = np.asarray(lengths).reshape(-1)
+    device = torch.device(device)
+    if device.type != "cuda":
+        return torch.from_numpy(np.ascontiguousarray(arr.astype(np.int32))).to(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), arr.size)
+    ring = _RINGS.get(key)
+    if ring is None:
+        ring = _RINGS[key] = _PinnedRing(arr.size)
+    return ring.stage(arr, device)
 
 
 def max_length(lengths) -> int:
@@ -245,9 +283,16 @@ def flat_layout(shapes):
     buffer in model.parameters() order; absent tensors (shape None) take no room.  Used for the flat
     gradient buffer produced by ``ModelForward.backward`` and for ``FusedTrainer``'s flat parameter /
     Adam-state buffers, so the two line up element for element."""
-    sizes = [0 if s is None else int(np.prod(s)) for s in shapes]
-    offsets = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])]).astype(np.int64)
-    return sizes, offsets
+    key = tuple(None if s is None else tuple(s) for s in shapes)
+    hit = _FLAT_LAYOUTS.get(key)          # computed once per model: this runs in every backward pass
+    if hit is None:
+        sizes = [0 if s is None else int(np.prod(s)) for s in shapes]
+        offsets = np.concatenate([[0], np.cumsum([(n + 3) // 4 * 4 for n in sizes])]).astype(np.int64)
+        hit = _FLAT_LAYOUTS[key] = (sizes, offsets)
+    return hit
+
+
+_FLAT_LAYOUTS: dict = {}
 
 
 class NLLLoss(torch.autograd.Function):
