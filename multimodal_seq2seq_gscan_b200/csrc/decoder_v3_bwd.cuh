@@ -855,6 +855,156 @@ __global__ void __launch_bounds__(256, 2) attn_value_z_kernel(ValueZP p) {
   }
 }
 
+// ---- the same sums on the tensor cores ------------------------------------------------------------------------------
+// Per example the two sums are ONE small product  Z_b [MT*16 x 6H] = W_b [MT*16 x Tt] . X_b [Tt x 6H]  with the rows of
+// W_b = (36 beta columns | Ti alpha columns | zeros) transposed: mma.sync m16n8k8 tf32 in split precision (W_lo X_hi +
+// W_hi X_lo + W_hi X_hi, truncation split: the raw word is the hi operand).  The FFMA2 kernel above issues 29 M warp
+// instructions (14 M of them FFMA2) and is bound by issue (64 us); this one issues 2.2 M MMAs + ~3 M others.
+//   grid (B, 3): CTA = (example, third of the 600 columns = 25 n-tiles);  160 threads = 5 warps x 5 n-tiles x MT m-tiles.
+//   W_b sits in shared memory ([MT*16][Tp + 4]: fragment loads conflict-free; split in registers), X streams through a
+//   per-warp cp.async rings of kZmStages stages of 8 steps x 40 columns (row pitch 40 = 8 mod 32: B fragments conflict-free).
+constexpr int kZmStages = 6, kZmCols = 200, kZmThreads = 160;
+inline size_t value_zm_smem_bytes(int T, int MT) {
+  const int Tp = (T + 7) & ~7;
+  return sizeof(float) * ((size_t)MT * 16 * (Tp + 4) + (size_t)kZmStages * 8 * kZmCols);
+}
+template <int MT>
+__global__ void __launch_bounds__(kZmThreads, 3) attn_value_zm_kernel(ValueZP p) {
+  extern __shared__ __align__(16) float zm_s[];
+  const int b = blockIdx.x, third = blockIdx.y, B = p.B, T = p.t_end - p.t_begin, Ti = p.Ti;
+  const int Tp = (T + 7) & ~7, nk = Tp / 8, ldw = Tp + 4;
+  float* w_s = zm_s;                                   // [MT*16][ldw]
+  float* ring = zm_s + (size_t)MT * 16 * ldw;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  // Every warp streams ITS 40 columns through a private ring (no block barrier in the loop: the warps drift apart and
+  // hide each other's waits).  Stage = steps [8 ks, 8 ks + 8) x 40 columns = 80 16-byte chunks, <= 3 per lane, the same
+  // (row in stage, column quad) every stage: source pointers and pitches are set up once (zero beyond T and for an
+  // absent dd: the ring slot is cleared instead)
+  constexpr int kWCols = 40, kChunks = 8 * (kWCols / 4), kPer = (kChunks + 31) / 32;
+  const int warp_ = tid >> 5, lane_ = tid & 31;
+  float* wring = ring + (size_t)warp_ * kZmStages * 8 * kWCols;
+  // Steps beyond T are NOT cleared: their weights are zero and the row read instead (the chunk's last valid step) is
+  // finite, so the loop body is one LDGSTS and one pointer add per chunk.  Columns without a source (dd of a model
+  // without conditional attention) are cleared once in every stage and never loaded.
+  const float* csrc[kPer];
+  size_t cstep[kPer];      // floats between consecutive stages (8 steps)
+  int coff[kPer], clast[kPer];   // clast: last stage whose row of this chunk is < T
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = lane_ + j * 32;
+    const int r = i / (kWCols / 4), c4 = i - r * (kWCols / 4);
+    const int col = third * kZmCols + warp_ * kWCols + 4 * c4;     // of the 600
+    coff[j] = r * kWCols + 4 * c4;
+    // rows of this chunk: r, r + 8, ...; if even the first is beyond T, read step 0 of the launch (its weight is zero)
+    const int r0 = r < T ? r : 0;
+    clast[j] = r < T ? (T - 1 - r) / 8 : -1;
+    const size_t row = (size_t)(p.t_begin + r0) * B + b;
+    csrc[j] = nullptr;
+    cstep[j] = 0;
+    if (i < kChunks) {
+      if (col < 4 * kH) { csrc[j] = p.dgates + row * (4 * kH) + col; cstep[j] = (size_t)8 * B * 4 * kH; }
+      else if (col < 5 * kH) { csrc[j] = p.dpre + row * kH + (col - 4 * kH); cstep[j] = (size_t)8 * B * kH; }
+      else if (p.NC > 5 * kH) { csrc[j] = p.dd + row * kH + (col - 5 * kH); cstep[j] = (size_t)8 * B * kH; }
+      if (!csrc[j])
+        for (int sgi = 0; sgi < kZmStages; ++sgi)
+          *reinterpret_cast<float4*>(wring + (size_t)sgi * 8 * kWCols + coff[j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  auto issue = [&](int ks) {
+    if (ks < nk) {
+      float* st = wring + (size_t)(ks % kZmStages) * 8 * kWCols;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        if (csrc[j]) {
+          cp_async16(st + coff[j], csrc[j]);
+          if (ks < clast[j]) csrc[j] += cstep[j];
+        }
+      }
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kZmStages - 1; ++s) issue(s);
+  // attention weights of this example, transposed (rows >= 36 + Ti and steps >= T are zero): 4-byte cp.async, one more
+  // group in flight beside the first stages of X - a load -> store loop here is ~40 dependent DRAM round trips.
+  // (t, m) advance by kZmThreads elements per iteration without a division.
+  {
+    constexpr int W = MT * 16, dT = kZmThreads / W, dM = kZmThreads - dT * W;
+    int t = tid / W, m = tid - t * W;
+    for (; t < Tp; ) {
+      float* dst = w_s + m * ldw + t;
+      if (t < T && m < kM) cp_async4(dst, p.beta + ((size_t)(p.t_begin + t) * B + b) * kM + m);
+      else if (t < T && m - kM < Ti) cp_async4(dst, p.alpha + ((size_t)(p.t_begin + t) * B + b) * Ti + (m - kM));
+      else *dst = 0.f;
+      t += dT; m += dM;
+      if (m >= W) { m -= W; ++t; }
+    }
+  }
+  cp_async_commit();
+  float acc[MT][5][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[mt][nt][c] = 0.f;
+  const int ncol0 = warp * 40;   // this warp's first column inside the CTA's 200
+  cp_async_wait<0>();
+  __syncthreads();                 // the weights (and the first stages) have landed for everybody
+  for (int ks = 0; ks < nk; ++ks) {
+    // groups in flight: this warp's stages ks .. ks + kZmStages - 2
+    cp_async_wait<kZmStages - 2>();
+    __syncwarp();                  // stage ks landed for the whole warp; stage ks - 1 is free (the warp computed it)
+    issue(ks + kZmStages - 1);
+    const float* st = wring + (size_t)(ks % kZmStages) * 8 * kWCols;
+    uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int o = (16 * mt + g) * ldw + 8 * ks + t4;
+      const float wv[4] = {w_s[o], w_s[o + 8 * ldw], w_s[o + 4], w_s[o + 8 * ldw + 4]};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {   // the tensor core reads the top 19 bits of the raw word: it IS the hi operand
+        ah[mt][c] = __float_as_uint(wv[c]);
+        al[mt][c] = __float_as_uint(wv[c] - __uint_as_float(ah[mt][c] & 0xffffe000u));
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt) {
+      const float x0 = st[t4 * kWCols + 8 * nt + g], x1 = st[(t4 + 4) * kWCols + 8 * nt + g];
+      const uint32_t bh0 = __float_as_uint(x0), bh1 = __float_as_uint(x1);
+      const uint32_t bl0 = __float_as_uint(x0 - __uint_as_float(bh0 & 0xffffe000u));
+      const uint32_t bl1 = __float_as_uint(x1 - __uint_as_float(bh1 & 0xffffe000u));
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], al[mt][0], al[mt][1], al[mt][2], al[mt][3], bh0, bh1);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bl0, bl1);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], bh0, bh1);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 5; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = 16 * mt + g + 8 * h;
+        const int c = third * kZmCols + ncol0 + 8 * nt + 2 * t4;
+        float2* dst = nullptr;
+        if (row < kM) {
+          if (c < p.ldv) dst = reinterpret_cast<float2*>(p.ZV + ((size_t)b * kM + row) * p.ldv + c);
+        } else if (row - kM < Ti) {
+          if (c < p.NC) dst = reinterpret_cast<float2*>(p.ZT + ((size_t)(row - kM) * B + b) * p.ldt + c);
+        }
+        if (dst) {
+          float2 o = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
+          if (p.accumulate) { const float2 old = *dst; o.x += old.x; o.y += old.y; }
+          *dst = o;
+        }
+      }
+}
+
 // Wst_V [5H][H] = [W_ih[:, 2H:3H] ; W_o2h[:, 3H:4H]],  Wst_T [6H][H] = [W_ih[:, H:2H] ; W_o2h[:, 2H:3H] ; W_c[:, H:2H]]
 __global__ void value_weight_stack_kernel(const float* __restrict__ W_ih, const float* __restrict__ W_o2h,
                                           const float* __restrict__ W_c, int H, float* __restrict__ WstV,

@@ -1290,6 +1290,25 @@ int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* com
     size_t smem = v3::value_z_smem_bytes(t1 - t0, Ti);
     // a shadow launch must not become resident next to a sweep CTA (194 KB of the SM's 227 KB): ask for at least 48 KB
     if (keep_off_sweep_sms && smem < 48 * 1024) smem = 48 * 1024;
+    // tensor-core form (GSCAN_Z_MMA=0: the FFMA2 kernel): 36 + Ti weight rows in 3 or 4 m-tiles of 16
+    static const bool z_mma = env_int("GSCAN_Z_MMA", 1) != 0;
+    if (z_mma && H == v3::kH && M == v3::kM) {
+      const int MT = (v3::kM + Ti + 15) / 16;
+      size_t zsm = v3::value_zm_smem_bytes(t1 - t0, MT);
+      if (keep_off_sweep_sms && zsm < 48 * 1024) zsm = 48 * 1024;
+      if (MT <= 4 && zsm <= kMaxSmemBytes) {
+        const dim3 g3(B, 3);
+        if (MT <= 3) {
+          if (zsm > 48 * 1024) TRY(set_smem(v3::attn_value_zm_kernel<3>, zsm));
+          v3::attn_value_zm_kernel<3><<<g3, v3::kZmThreads, zsm, s_>>>(zp);
+        } else {
+          if (zsm > 48 * 1024) TRY(set_smem(v3::attn_value_zm_kernel<4>, zsm));
+          v3::attn_value_zm_kernel<4><<<g3, v3::kZmThreads, zsm, s_>>>(zp);
+        }
+        GSCAN_CHECK_LAUNCH();
+        return 0;
+      }
+    }
     const dim3 zgrid(B, ceil_div(zNC / 4, 64));
     if (v3::value_z_qw(Ti) == 3) {
       if (v3::value_z_smem_bytes(Tt, Ti) > 48 * 1024) TRY(set_smem(v3::attn_value_z_kernel<3>, v3::value_z_smem_bytes(Tt, Ti)));
