@@ -234,6 +234,11 @@ struct DecFwd3P {
   const float* Xe;                // [T][B][4H]
   float *U, *Cs, *gates, *alpha, *beta, *Qp, *qT, *qV, *beta_sum;   // saved activations (recurrent.cuh DecFwdP)
   long long* timeline;   // debug: [T][16 stamps][16 warps] clock64 stamps of CTA 0 (lane 0 of every warp), else null
+  // progress signals (training sweep): every CTA adds 1 to progress[k] once all its stores of the steps t <= t_signal[k]
+  // (row groups <= t_signal[k] + 1 of U) are visible: the output head of those rows then runs beside the rest of the sweep
+  unsigned int* progress;   // [n_signals] words, zeroed by the host; null: no signals
+  int n_signals;
+  int t_signal[4];          // ascending
   // greedy decoding (predict.py:97-117); tables as in recurrent.cuh DecFwdP
   const float *XeTab, *OutE, *Wo_t;
   int V, Vp, sos, eos;
@@ -803,6 +808,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     if (lane == 0) flag_s[0] = any != 0u;
   };
 
+  int sig_prev = -1;   // signal to publish for the previous step (its stores were issued by the I/O warps at its end)
   for (int t = 0; t < p.T; ++t) {
     const size_t row0 = (size_t)t * B + b0;   // + n
     const uint32_t par = (uint32_t)(t & 1);
@@ -896,7 +902,9 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     GSCAN3_STAMP(19);
+    if (!GREEDY && sig_prev >= 0 && ioT) __threadfence();   // the I/O threads issued every store of the previous step
     __syncthreads();
+    if (!GREEDY && sig_prev >= 0 && tid == 0) atomicAdd(p.progress + sig_prev, 1u);
     GSCAN3_STAMP(5);
     if (ioT) {   // alpha rows of the examples this rank writes (Ti floats each: no 16-byte granularity in general)
       for (int f = io; f < kNB * Ti; f += kIoThreadsF) {
@@ -1136,6 +1144,14 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       io_rows(0, out_s, kOutRow, 20, p.gates, row0, H4, true);
       io_rows(160, out_s + 4 * kHS, kOutRow, 5, p.U + kH, row0 + B, H4, false);   // h_t: row group t + 1 of U
       io_rows(200, out_s + 5 * kHS, kOutRow, 5, p.Cs, row0 + B, kH, false);      // c_t: row group t + 1 of Cs
+    }
+    if (!GREEDY) {   // published at the first block barrier of the next step (cut points are < T - 1)
+      sig_prev = -1;
+      if (p.progress != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (k < p.n_signals && t == p.t_signal[k]) sig_prev = k;
+      }
     }
     GSCAN3_STAMP(14);
     if (GREEDY) {

@@ -148,6 +148,7 @@ struct Layout {
   size_t Wcomb;               // [RB][H] = [W_c[:, H:2H] ; W_ih[:, H:2H]] . W_kT: P straight from the encoder outputs
   size_t U, Xe, Cs, gates, alpha, beta, Qp, qT, qV, beta_sum, aux_logp, pre, logp;
   size_t tag;                  // which decoder sweep the forward call ran (checked by the v3 backward kernel)
+  size_t progress_f;           // progress words of the forward sweep (output head in its shadow)
   // backward scratch
   size_t dlogits, dpre, dU, dgates, dd, dqV, dqT, dKT, dKV, dh0, dbeta_aux, dfeat, dconv, dWt_cnn;
   size_t denc_out, dh_enc, dpre0, dga[2], hprev[2], denc_x, dvec;
@@ -198,6 +199,7 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
   L.pre = L.take(Tt * B * H);
   L.logp = L.take(B * Tt * V);
   L.tag = L.take(4);
+  L.progress_f = L.take(4);
   if (with_backward) {
     L.dlogits = L.take(Tt * B * V);
     L.dpre = L.take(Tt * B * H);
@@ -1098,14 +1100,15 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   bool v3_done = false;
   // output projection + log-softmax of the steps [t0, t1) (rows t0*B .. t1*B of the time-major lists)
   const size_t head_smem = (size_t)V * (H + 1) * sizeof(float);
-  if (head_smem > 48 * 1024) TRY(set_smem(out_logsoftmax_kernel, head_smem));
+  TRY(set_smem(out_logsoftmax_kernel, head_smem > 80 * 1024 ? head_smem : (size_t)80 * 1024));
   // keep_off_sweep_sms: a shadow launch must not land on the SMs of the sweep (its CTAs would share their issue slots
   // with the latency-bound recurrence: measured +45 us on the sweep) - asking for 48 KB of shared memory makes the
   // CTAs fit only where the sweep (185 KB) is not resident
   auto head_rows = [&](int t0, int t1, cudaStream_t s_, bool keep_off_sweep_sms = false) -> int {
     const long r0 = (long)t0 * B, r1 = (long)t1 * B;
     if (r1 <= r0) return 0;
-    const size_t head_smem_l = keep_off_sweep_sms && head_smem < 48 * 1024 ? (size_t)48 * 1024 : head_smem;
+    // (the forward sweep holds 150 KB of an SM's 227 KB: 80 KB do not fit beside it)
+    const size_t head_smem_l = keep_off_sweep_sms && head_smem < 80 * 1024 ? (size_t)80 * 1024 : head_smem;
     TRY(linear(U1 + (size_t)r0 * 4 * H, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre + (size_t)r0 * H, H, (int)(r1 - r0), H,
                4 * H, nullptr, nullptr, 0, s_));
     const int blocks = min(ceil_div((int)(r1 - r0), 8), 8 * num_sms());
@@ -1114,6 +1117,8 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     GSCAN_CHECK_LAUNCH();
     return 0;
   };
+  int head_t0 = 0;               // first step whose output head is still to do after the sweep
+  bool fwd_shadow_used = false;
   if (v3_shape_ok(*d)) {
     v3::DecFwd3P p3{};
     p3.B = B; p3.T = Tt; p3.Ti = d->Ti;
@@ -1121,9 +1126,60 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     p3.KT = p.KT; p3.KV = p.KV; p3.cmd_len = cmd_len; p3.h_init = p.h_init; p3.c_init = p.c_init; p3.Xe = p.Xe;
     p3.U = p.U; p3.Cs = p.Cs; p3.gates = p.gates; p3.alpha = p.alpha; p3.beta = p.beta;
     p3.Qp = p.Qp; p3.qT = p.qT; p3.qV = p.qV; p3.beta_sum = p.beta_sum;
+    // Shadow schedule of the output head: the sweep holds 125 of the 148 SMs for ~0.67 ms and completes the rows of
+    // [e | h | c_T | c_V] step by step.  Once every CTA has published the steps < cut (a counter in the workspace,
+    // awaited by helper stream 2 through cuStreamWaitValue32) the output projection and the log-softmax of THOSE rows
+    // run on the idle SMs beside the rest of the sweep; only the steps >= the last cut are left for after it.
+    // (Round 1 tried this with the compute warps signalling: the signal code cost the sweep 33 us.  Now the I/O warps,
+    // off the critical path, fence and one thread adds at a barrier that exists anyway.)
+    int f_cut[4];
+    int nf = 0;
+    {
+      const char* spec = getenv("GSCAN_FWD_SHADOW_CUTS");
+      if (!spec) spec = "30,60,85";
+      int prev = 0;
+      for (const char* q = spec; *q && nf < 4;) {
+        const int pct = atoi(q);
+        const int t = pct * Tt / 100;
+        if (pct > 0 && pct < 100 && t > prev && t < Tt) { f_cut[nf++] = t; prev = t; }
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+    }
+    const int sweep_ctas_f = ceil_div(B, v3::kNB) * v3::kC;
+    const int idle_f = num_sms() - sweep_ctas_f;
+    bool fshadow = S && stream_wait_value_fn() && env_int("GSCAN_FWD_SHADOW", 1) != 0 && Tt >= 16 && idle_f >= 8 && nf > 0;
+    unsigned int* progress_f = reinterpret_cast<unsigned int*>(ws + L.progress_f);
+    if (fshadow) {
+      TRYCUDA(cudaMemsetAsync(progress_f, 0, 4 * sizeof(unsigned int), st));
+      p3.progress = progress_f;
+      p3.n_signals = nf;
+      for (int k = 0; k < nf; ++k) p3.t_signal[k] = f_cut[k] - 1;
+      TRY(fork_side(S, 2, st));   // helper stream 2 starts from here, NOT from the end of the sweep
+    }
     int rc = launch_dec_fwd_v3(*d, P, ws, L, p3, false, st, par_tail);
     if (rc == 0) v3_done = true;
     else if (rc != GSCAN_E_UNSUPPORTED) return rc;
+    if (fshadow && !v3_done) {   // nobody will signal
+      fshadow = false;
+      TRY(join_side(S, 2, st));
+    }
+    if (fshadow) {
+      cudaStream_t sh = S->s[2];
+      tc::ScopedSmCap cap(idle_f);
+      for (int k = 0; k < nf; ++k) {
+        if (stream_wait_value_fn()((CUstream)sh, (CUdeviceptr)(progress_f + k), (cuuint32_t)sweep_ctas_f, 0u /* GEQ */) !=
+            CUDA_SUCCESS) {
+          if (k > 0) { join_side(S, 2, st); return GSCAN_E_UNSUPPORTED; }
+          fshadow = false;          // stream memory operations unavailable: everything after the sweep
+          TRY(join_side(S, 2, st));
+          break;
+        }
+        TRY(head_rows(k == 0 ? 0 : f_cut[k - 1], f_cut[k], sh, true));
+      }
+      if (fshadow) head_t0 = f_cut[nf - 1];
+    }
+    fwd_shadow_used = fshadow;
   }
   if (v3_done) {
   } else if (cc.C) {
@@ -1143,7 +1199,8 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   chain_mark("m:sweep_done", st);
   // output projection for all steps at once, then log-softmax.  (Chunks of it in the shadow of the forward sweep, the
   // way the backward pass does it, were a net loss: DESIGN.md 4.5 - and the signal code alone cost the sweep 33 us.)
-  TRY(head_rows(0, Tt, st));
+  TRY(head_rows(head_t0, Tt, st));
+  if (fwd_shadow_used) TRY(join_side(S, 2, st));
   TRYCUDA(cudaMemcpyAsync(logp, ws + L.logp, sizeof(float) * (size_t)B * Tt * V, cudaMemcpyDeviceToDevice, st));
   if (d->auxiliary_task) {
     row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(ws + L.beta_sum, M, B, ws + L.aux_logp);
