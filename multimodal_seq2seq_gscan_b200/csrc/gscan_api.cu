@@ -1027,6 +1027,7 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
 
   prof_mark(0, st);
   chain_mark("fwd_start", st);
+  TRYCUDA(cudaMemsetAsync(ws + L.progress_f, 0, 4 * sizeof(unsigned int), st));   // progress words of the sweep (far ahead of it)
   // Three chains before the sweep: the command encoder (a long chain of small kernels: high-priority helper stream 1,
   // issued first), the decoder prelude (depends on targets and weights only; one big GEMM, capped: high-priority
   // helper stream 0) and the situation CNN (wide kernels of small CTAs that co-reside with the GEMM's: the caller's
@@ -1112,8 +1113,9 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     TRY(linear(U1 + (size_t)r0 * 4 * H, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre + (size_t)r0 * H, H, (int)(r1 - r0), H,
                4 * H, nullptr, nullptr, 0, s_));
     const int blocks = min(ceil_div((int)(r1 - r0), 8), 8 * num_sms());
+    // (the caller's copy of the log-probabilities is written here too: no copy kernel between the head and the loss)
     out_logsoftmax_kernel<<<blocks, 256, head_smem_l, s_>>>(ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.logp, nullptr,
-                                                            r0, r1);
+                                                            r0, r1, logp);
     GSCAN_CHECK_LAUNCH();
     return 0;
   };
@@ -1136,7 +1138,7 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     int nf = 0;
     {
       const char* spec = getenv("GSCAN_FWD_SHADOW_CUTS");
-      if (!spec) spec = "30,60,85";
+      if (!spec) spec = "25,50,72,90";
       int prev = 0;
       for (const char* q = spec; *q && nf < 4;) {
         const int pct = atoi(q);
@@ -1151,8 +1153,7 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     bool fshadow = S && stream_wait_value_fn() && env_int("GSCAN_FWD_SHADOW", 1) != 0 && Tt >= 16 && idle_f >= 8 && nf > 0;
     unsigned int* progress_f = reinterpret_cast<unsigned int*>(ws + L.progress_f);
     if (fshadow) {
-      TRYCUDA(cudaMemsetAsync(progress_f, 0, 4 * sizeof(unsigned int), st));
-      p3.progress = progress_f;
+      p3.progress = progress_f;   // (zeroed at the top of the call)
       p3.n_signals = nf;
       for (int k = 0; k < nf; ++k) p3.t_signal[k] = f_cut[k] - 1;
       TRY(fork_side(S, 2, st));   // helper stream 2 starts from here, NOT from the end of the sweep
@@ -1201,7 +1202,6 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   // way the backward pass does it, were a net loss: DESIGN.md 4.5 - and the signal code alone cost the sweep 33 us.)
   TRY(head_rows(head_t0, Tt, st));
   if (fwd_shadow_used) TRY(join_side(S, 2, st));
-  TRYCUDA(cudaMemcpyAsync(logp, ws + L.logp, sizeof(float) * (size_t)B * Tt * V, cudaMemcpyDeviceToDevice, st));
   if (d->auxiliary_task) {
     row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(ws + L.beta_sum, M, B, ws + L.aux_logp);
     GSCAN_CHECK_LAUNCH();
@@ -1249,6 +1249,10 @@ int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* com
   float* U0 = ws + L.U;
   float* U1 = ws + L.U + (size_t)B * 4 * H;
 
+  SideStreams* S = side_streams();
+  // helper stream 2 starts here: it zeroes the destinations of the weight-gradient GEMMs beside the output-head work
+  // (the caller's stream waits for that before the sweep), then runs the shadow launches
+  if (S) TRY(fork_side(S, 2, st));
   // B1: log-softmax backward, hidden_to_output
   prof_mark(5, st);
   const bool head_fused = V <= kHeadMaxV && H <= 128 && getenv("GSCAN_HEAD_UNFUSED") == nullptr;
@@ -1268,7 +1272,6 @@ int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* com
   // it, on helper stream 1 beside the other post-sweep chains.  (Running them on a helper stream BEFORE the sweep
   // delays the cluster launch of the sweep behind the persistent GEMM: measured 1.11 -> 1.45 ms for the sweep.)
   TRY(matmul_nn(ws + L.dpre, H, P[GSCAN_P_O2H_W], 4 * H, ws + L.dU, 4 * H, R, 4 * H, H, 0, st));
-  SideStreams* S = side_streams();
   // B3: auxiliary head
   const float* dbeta_aux = nullptr;
   if (d->auxiliary_task && d_aux_logp) {
@@ -1386,9 +1389,11 @@ int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* com
   const int group_chunks = shadow_z ? min(n_cut, env_int("GSCAN_SHADOW_GROUP_CHUNKS", 2)) : n_cut;
   unsigned int* progress = reinterpret_cast<unsigned int*>(ws + L.progress);
   if (shadow) {
-    TRYCUDA(cudaMemsetAsync(progress, 0, 4 * sizeof(unsigned int), st));
-    TRY(tc::launch_group_zero(gp, ngp, st));
-    TRY(fork_side(S, 2, st));   // helper stream 2 starts from here, NOT from the end of the sweep
+    cudaStream_t z = S->s[2];     // forked at the top of the call, NOT from the end of the sweep
+    TRYCUDA(cudaMemsetAsync(progress, 0, 4 * sizeof(unsigned int), z));
+    TRY(tc::launch_group_zero(gp, ngp, z));
+    TRYCUDA(cudaEventRecord(S->aux_ev[1], z));
+    TRYCUDA(cudaStreamWaitEvent(st, S->aux_ev[1], 0));   // before the sweep (and the post-sweep group launch)
   }
   prof_mark(6, st);
   bool bwd_v3 = false;
@@ -1620,7 +1625,7 @@ int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* com
   if (S) {
     TRY(join_side(S, 0, st));
     TRY(join_side(S, 1, st));
-    if (shadow || sw != stx) TRY(join_side(S, 2, st));
+    TRY(join_side(S, 2, st));   // forked at the top of the call
   }
   prof_mark(9, st);
   chain_mark("joined", st);

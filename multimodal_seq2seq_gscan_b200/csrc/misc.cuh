@@ -158,7 +158,8 @@ constexpr int kMaxVPerLane = 4;
 __global__ void __launch_bounds__(256) out_logsoftmax_kernel(const float* __restrict__ pre, const float* __restrict__ Wh2o,
                                                              int H, int V, int B, int T, float* __restrict__ logp,
                                                              float* __restrict__ logits_out /* [R][V] or null */,
-                                                             long row_begin = 0, long row_end = -1) {
+                                                             long row_begin = 0, long row_end = -1,
+                                                             float* __restrict__ logp2 = nullptr /* second copy of logp */) {
   extern __shared__ __align__(16) float w_s[];   // [V][H+1]
   for (int i = threadIdx.x; i < V * H; i += blockDim.x) w_s[(i / H) * (H + 1) + (i % H)] = __ldg(Wh2o + i);
   __syncthreads();
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256) out_logsoftmax_kernel(const float* __rest
       int v = lane + 32 * i;
       if (v < V) {
         if (logp) logp[((long)b * T + t) * V + v] = (l[i] - mx) - lse;
+        if (logp2) logp2[((long)b * T + t) * V + v] = (l[i] - mx) - lse;
         if (logits_out) logits_out[row * V + v] = l[i];
       }
     }

@@ -300,7 +300,7 @@ class NLLLoss(torch.autograd.Function):
     (gscan_nll_forward / _backward)."""
 
     @staticmethod
-    def forward(ctx, logp, targets, pad_idx, shift):
+    def forward(ctx, logp, targets, pad_idx, shift, clone_out=True):
         lib = _lib.load()
         _require_cuda(logp, targets)
         ctx.set_materialize_grads(False)
@@ -313,15 +313,18 @@ class NLLLoss(torch.autograd.Function):
         _call_counts["other"] += 1
         ctx.save_for_backward(targets, out)
         ctx.meta = (B, T, V, int(pad_idx), int(shift))
-        count = out[1].clone()
+        # The reference's driver updates the loss in place (train.py:107), which autograd forbids on an output that is
+        # a view of a buffer made here: by default the mean is a copy.  The fused trainer never does and takes views
+        # (clone_out=False): no copy kernels between the head and the backward pass.
+        count = out[1]
         ctx.mark_non_differentiable(count)
-        return out[0].clone(), count
+        return (out[0].clone() if clone_out else out[0]), count
 
     @staticmethod
     def backward(ctx, d_loss, _d_count):
         lib = _lib.load()
         if d_loss is None:
-            return None, None, None, None
+            return None, None, None, None, None
         targets, out = ctx.saved_tensors
         B, T, V, pad_idx, shift = ctx.meta
         d_loss = d_loss.contiguous().float().reshape(1)
@@ -329,7 +332,7 @@ class NLLLoss(torch.autograd.Function):
         _lib.check(lib.gscan_nll_backward(_ptr(targets), B, T, V, pad_idx, shift, _ptr(out), _ptr(d_loss), _ptr(d_logp),
                                           _stream(out.device)), "gscan_nll_backward")
         _call_counts["other"] += 1
-        return d_logp, None, None, None
+        return d_logp, None, None, None, None
 
 
 def metrics_counts(logp: torch.Tensor, targets: torch.Tensor, pad_idx: int) -> torch.Tensor:

@@ -102,7 +102,7 @@ class FusedTrainer:
                 global_counts, counts_work = dp.start_count_allreduce(targets, model.target_pad_idx, self.group)
         logp, aux = model(commands_input=commands, commands_lengths=commands_lengths, situations_input=situations,
                           target_batch=targets, target_lengths=target_lengths)
-        nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1)
+        nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1, False)
         aux_mean = model.get_auxiliary_loss(aux, target_positions) if use_aux else None
         if self.distributed:
             if counts_work is not None:
