@@ -207,6 +207,14 @@ int gscan_nll_backward(const int64_t* targets, int32_t B, int32_t Tt, int32_t V,
                        int32_t shift, const float* loss_out /* [2] from forward */,
                        const float* d_loss /* [1] */, float* d_logp /* [B,Tt,V], overwritten */,
                        void* stream);
+/*
+ * The number of scored entries alone (loss_out[1]; loss_out[0] = 0), from the targets: with it gscan_nll_backward can
+ * form d_logp BEFORE the forward pass has produced logp (the gradient of a mean or sum of NLL terms does not depend on
+ * their values).  The fused trainer does this so that nothing but the output head stands between the two sweeps;
+ * reference semantics: model.py:100 (NLLLoss(ignore_index)) and train.py:102-107.
+ */
+int gscan_nll_count(const int64_t* targets, int32_t B, int32_t Tt, int32_t pad_idx, int32_t shift,
+                    float* loss_out /* [2] */, void* stream);
 
 /*
  * Model.get_metrics (reference model.py:117-137) without host syncs:

@@ -72,6 +72,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "gscan_nll_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                     c_void_p]),
+    "gscan_nll_count": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "gscan_nll_backward": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
     "gscan_metrics": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

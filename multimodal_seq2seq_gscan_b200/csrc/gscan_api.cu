@@ -1787,6 +1787,15 @@ int gscan_nll_forward(const float* logp, const int64_t* targets, int32_t B, int3
   return GSCAN_OK;
 }
 
+int gscan_nll_count(const int64_t* targets, int32_t B, int32_t Tt, int32_t pad_idx, int32_t shift, float* loss_out,
+                    void* stream) {
+  if (!targets || !loss_out || shift < 0 || B < 1 || Tt < 1) return GSCAN_E_BADARG;
+  nll_count_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(targets), B, Tt, pad_idx, shift,
+                                                         loss_out);
+  GSCAN_CHECK_LAUNCH();
+  return GSCAN_OK;
+}
+
 int gscan_nll_backward(const int64_t* targets, int32_t B, int32_t Tt, int32_t V, int32_t pad_idx, int32_t shift,
                        const float* loss_out, const float* d_loss, float* d_logp, void* stream) {
   if (!targets || !loss_out || !d_loss || !d_logp || shift < 0) return GSCAN_E_BADARG;

@@ -384,6 +384,28 @@ __global__ void nll_final_kernel(float* __restrict__ out, int nblocks) {
   if (lane == 0) { out[0] = sum / cnt; out[1] = cnt; }
 }
 
+// out[1] = number of scored entries (what nll_forward_kernel counts), out[0] = 0: the targets alone decide it, so the
+// gradient of the loss with respect to the log-probabilities can be formed before the forward pass has run
+__global__ void __launch_bounds__(1024) nll_count_kernel(const long long* __restrict__ tgt, int B, int T, int pad, int shift,
+                                                         float* __restrict__ out) {
+  __shared__ float s_cnt[32];
+  float cnt = 0.f;
+  const long R = (long)B * T;
+  for (long r = threadIdx.x; r < R; r += blockDim.x) {
+    const int b = r / T, t = r - (long)b * T;
+    const long long y = (t + shift < T) ? tgt[(long)b * T + t + shift] : (shift > 0 ? 0 : pad);   // see nll_forward_kernel
+    cnt += y != pad ? 1.f : 0.f;
+  }
+  cnt = warp_sum(cnt);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float c = threadIdx.x < (blockDim.x >> 5) ? s_cnt[threadIdx.x] : 0.f;
+    c = warp_sum(c);   // integers below 2^24: exact in any order
+    if (threadIdx.x == 0) { out[0] = 0.f; out[1] = c; }
+  }
+}
+
 __global__ void nll_backward_kernel(const long long* __restrict__ tgt, int B, int T, int V, int pad, int shift,
                                     const float* __restrict__ loss_out, const float* __restrict__ d_loss,
                                     float* __restrict__ d_logp) {

@@ -234,10 +234,11 @@ class ModelForward(torch.autograd.Function):
         # returned to autograd are views into it (this is also the data-parallel all-reduce buffer)
         sizes, offsets = flat_layout(ctx.param_shapes)
         n_flat = int(offsets[-1])
+        prezeroed = _flat_grad_prezeroed
         flat = _take_flat_grad_target(n_flat, dev)
         if flat is None:
             flat = torch.zeros(n_flat + FLAT_TAIL, dtype=torch.float32, device=dev)
-        else:
+        elif not prezeroed:
             flat[:n_flat].zero_()      # the tail (data-parallel counts) belongs to the caller
         views = [None if s is None else flat[int(o):int(o) + n].view(s)
                  for s, o, n in zip(ctx.param_shapes, offsets[:-1], sizes)]
@@ -258,15 +259,18 @@ class ModelForward(torch.autograd.Function):
 # that gradients and counts travel in ONE all-reduce (dp.COUNT_SLOTS)
 FLAT_TAIL = 4
 _flat_grad_target: Optional[torch.Tensor] = None
+_flat_grad_prezeroed = False
 
 
-def set_flat_grad_target(buf: Optional[torch.Tensor]) -> None:
+def set_flat_grad_target(buf: Optional[torch.Tensor], prezeroed: bool = False) -> None:
     """The NEXT ``ModelForward.backward`` writes its flat gradient into ``buf`` (fp32, at least
     ``flat_layout(...)[1][-1] + FLAT_TAIL`` elements; only the gradient part is zeroed) instead of a fresh
     tensor.  ``FusedTrainer`` hands in its persistent buffer: no allocation per step, and the counts it has
-    already written into the tail survive."""
-    global _flat_grad_target
+    already written into the tail survive.  ``prezeroed``: the caller has zeroed the gradient part already
+    (the trainer does it at the start of the step, off the path between the two sweeps)."""
+    global _flat_grad_target, _flat_grad_prezeroed
     _flat_grad_target = buf
+    _flat_grad_prezeroed = bool(prezeroed) and buf is not None
 
 
 def _take_flat_grad_target(n_flat: int, device) -> Optional[torch.Tensor]:
@@ -333,6 +337,35 @@ class NLLLoss(torch.autograd.Function):
                                           _stream(out.device)), "gscan_nll_backward")
         _call_counts["other"] += 1
         return d_logp, None, None, None, None
+
+
+def nll_grad_from_targets(targets: torch.Tensor, V: int, pad_idx: int, shift: int, sum_form: bool):
+    """d(loss)/d(logp) of the mean (``sum_form`` False) or the sum of the NLL terms ``NLLLoss`` scores, formed from the
+    targets alone (gscan_nll_count + gscan_nll_backward) - bit-identical to what ``NLLLoss.backward`` returns for
+    ``loss = mean`` resp. ``loss = mean * count``.  Returns (d_logp [B, T, V], result buffer with the count at [1])."""
+    lib = _lib.load()
+    _require_cuda(targets)
+    targets = targets.contiguous()
+    B, T = targets.shape
+    dev = targets.device
+    out = torch.empty(68, dtype=torch.float32, device=dev)
+    _lib.check(lib.gscan_nll_count(_ptr(targets), B, T, int(pad_idx), int(shift), _ptr(out), _stream(dev)), "gscan_nll_count")
+    d_logp = torch.empty(B, T, V, dtype=torch.float32, device=dev)
+    d_loss = out[1:2] if sum_form else _ones1(dev)     # d loss / d mean = count, resp. 1
+    _lib.check(lib.gscan_nll_backward(_ptr(targets), B, T, V, int(pad_idx), int(shift), _ptr(out), _ptr(d_loss), _ptr(d_logp),
+                                      _stream(dev)), "gscan_nll_backward")
+    _call_counts["other"] += 2
+    return d_logp, out
+
+
+_ONES1: dict = {}
+
+
+def _ones1(dev) -> torch.Tensor:
+    t = _ONES1.get(dev)
+    if t is None:
+        t = _ONES1[dev] = torch.ones(1, dtype=torch.float32, device=dev)
+    return t
 
 
 def metrics_counts(logp: torch.Tensor, targets: torch.Tensor, pad_idx: int) -> torch.Tensor:

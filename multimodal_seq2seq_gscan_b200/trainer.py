@@ -44,6 +44,7 @@ class FusedTrainer:
         # persistent flat gradient buffer: [gradients in parameters() order | n_tok, n_examples, 0, 0]; the backward
         # pass writes into it (ops.set_flat_grad_target), the data-parallel all-reduce sums all of it at once
         self.flat_grad = torch.zeros(n + dp.COUNT_SLOTS, dtype=torch.float32, device=dev)
+        self._side_stream = torch.cuda.Stream(device=dev)   # zeroing, early loss gradient, loss value (train_step)
         self._one = torch.ones((), dtype=torch.float32, device=dev)   # d loss / d loss, without a fill kernel per step
         # re-seat every parameter as a view into the flat buffer (identity of the nn.Parameter kept)
         with torch.no_grad():
@@ -100,21 +101,52 @@ class FusedTrainer:
             self.flat_grad[n:n + 2].copy_(local)
             if use_aux and global_counts is None:
                 global_counts, counts_work = dp.start_count_allreduce(targets, model.target_pad_idx, self.group)
+        # Off the critical path, on a second stream beside the forward pass: the zeroing of the gradient buffer
+        # (ModelForward.backward is told so below) and - without the auxiliary task - d(loss)/d(logp), which depends on the
+        # targets only (-1/N_tok, resp. -1 in SUM form, at the scored positions).  Between the two sweeps of the step
+        # there is then nothing but the output head; the loss VALUE (reporting only) is computed on that stream too,
+        # beside the backward pass.
+        main = torch.cuda.current_stream(self.flat_param.device)
+        side = self._side_stream
+        early_grad = not use_aux
+        side.wait_stream(main)           # the previous step's Adam has read the gradient buffer; the targets are there
+        with torch.cuda.stream(side):
+            self.flat_grad[:n].zero_()
+            if early_grad:
+                d_logp, _ = ops.nll_grad_from_targets(targets, int(model._static_cfg["V"]), model.target_pad_idx, 1,
+                                                      sum_form=self.distributed)
+                d_logp.record_stream(main)
         logp, aux = model(commands_input=commands, commands_lengths=commands_lengths, situations_input=situations,
                           target_batch=targets, target_lengths=target_lengths)
-        nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1, False)
-        aux_mean = model.get_auxiliary_loss(aux, target_positions) if use_aux else None
-        if self.distributed:
-            if counts_work is not None:
-                counts_work.wait()
-            loss = dp.sum_loss(nll, n_tok, aux_mean, targets.shape[0], self.weight_target_loss, global_counts)
+        main.wait_stream(side)
+        if early_grad:
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(main)
+            ops.set_flat_grad_target(self.flat_grad, prezeroed=True)
+            try:
+                grads = torch.autograd.grad([logp], self._present, grad_outputs=[d_logp])
+            finally:
+                ops.set_flat_grad_target(None)
+            with torch.cuda.stream(side), torch.no_grad():
+                side.wait_event(fwd_done)
+                logp.record_stream(side)
+                nll, n_tok = ops.NLLLoss.apply(logp.detach(), targets, model.target_pad_idx, 1, False)
+                loss = nll * n_tok if self.distributed else nll
+                loss.record_stream(main)
         else:
-            loss = dp.global_loss(nll, aux_mean, self.weight_target_loss)
-        ops.set_flat_grad_target(self.flat_grad)
-        try:
-            grads = torch.autograd.grad(loss, self._present, grad_outputs=self._one)
-        finally:
-            ops.set_flat_grad_target(None)
+            nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1, False)
+            aux_mean = model.get_auxiliary_loss(aux, target_positions)
+            if self.distributed:
+                if counts_work is not None:
+                    counts_work.wait()
+                loss = dp.sum_loss(nll, n_tok, aux_mean, targets.shape[0], self.weight_target_loss, global_counts)
+            else:
+                loss = dp.global_loss(nll, aux_mean, self.weight_target_loss)
+            ops.set_flat_grad_target(self.flat_grad, prezeroed=True)
+            try:
+                grads = torch.autograd.grad(loss, self._present, grad_outputs=self._one)
+            finally:
+                ops.set_flat_grad_target(None)
         flat_grad = self._flat_gradient(grads)
         denom = None
         if self.distributed:
@@ -132,6 +164,7 @@ class FusedTrainer:
         self.step_count += 1
         ops.adam_step(self.flat_param, flat_grad[:n], self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1],
                       self.eps, self.step_count, grad_denom=denom)
+        main.wait_stream(side)           # the loss value (and nothing else) comes from the second stream
         model.update_state(is_best=False)
         self.last_logp, self.last_aux = logp.detach(), aux
         self.last_flat_grad = flat_grad
