@@ -444,6 +444,8 @@ def measure_training(wl, steps, warmup, flush, barrier, dist, lib):
     barrier()
     launches = lib.gscan_launch_count() - launches0
     per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    if os.environ.get("GSCAN_BENCH_DEBUG"):
+        print("[bench] per-step ms:", " ".join("%.3f" % x for x in per_step), file=sys.stderr)
     total_ms = torch.tensor([sum(per_step)], dtype=torch.float64, device=wl.dev)
     wl.dp_timeline = None
     if wl.distributed:

@@ -808,7 +808,6 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     if (lane == 0) flag_s[0] = any != 0u;
   };
 
-  int sig_prev = -1;   // signal to publish for the previous step (its stores were issued by the I/O warps at its end)
   for (int t = 0; t < p.T; ++t) {
     const size_t row0 = (size_t)t * B + b0;   // + n
     const uint32_t par = (uint32_t)(t & 1);
@@ -902,9 +901,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       }
     }
     GSCAN3_STAMP(19);
-    if (!GREEDY && sig_prev >= 0 && ioT) __threadfence();   // the I/O threads issued every store of the previous step
     __syncthreads();
-    if (!GREEDY && sig_prev >= 0 && tid == 0) atomicAdd(p.progress + sig_prev, 1u);
     GSCAN3_STAMP(5);
     if (ioT) {   // alpha rows of the examples this rank writes (Ti floats each: no 16-byte granularity in general)
       for (int f = io; f < kNB * Ti; f += kIoThreadsF) {
@@ -1144,13 +1141,20 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       io_rows(0, out_s, kOutRow, 20, p.gates, row0, H4, true);
       io_rows(160, out_s + 4 * kHS, kOutRow, 5, p.U + kH, row0 + B, H4, false);   // h_t: row group t + 1 of U
       io_rows(200, out_s + 5 * kHS, kOutRow, 5, p.Cs, row0 + B, kH, false);      // c_t: row group t + 1 of Cs
-    }
-    if (!GREEDY) {   // published at the first block barrier of the next step (cut points are < T - 1)
-      sig_prev = -1;
+      // Progress signal: these were the last stores of step t, and every store of the step was issued by an I/O thread.
+      // Fence by the writers, a barrier among the 256 I/O threads only (named barrier 3), one add per CTA - all of it in
+      // the I/O warps' shadow.  (At a block barrier of the next step the same code cost the sweep 18 us: a fence in the
+      // instruction stream of the compute warps, taken or not, pins the memory operations around it.)
       if (p.progress != nullptr) {
+        int sig = -1;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (k < p.n_signals && t == p.t_signal[k]) sig_prev = k;
+          if (k < p.n_signals && t == p.t_signal[k]) sig = k;
+        if (sig >= 0) {
+          __threadfence();
+          asm volatile("bar.sync 3, %0;" ::"n"(kIoThreadsF) : "memory");
+          if (io == 0) atomicAdd(p.progress + sig, 1u);
+        }
       }
     }
     GSCAN3_STAMP(14);

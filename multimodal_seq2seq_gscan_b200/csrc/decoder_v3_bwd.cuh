@@ -335,7 +335,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
     }
   };
 
-  int it = 0, sig_prev = -1;
+  int it = 0;
   for (int t = p.T - 1; t >= 0; --t, ++it) {
     const size_t row0 = (size_t)t * B + b0;
     const uint32_t par = (uint32_t)(it & 1);
@@ -386,10 +386,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
       dUcT_s[cn * kHS + chh] = c_dUcT;
       c_cnew = c_cprev;   // c_{t-1} is the "new" cell state of the step about to come
     }
-    // the progress signal of the PREVIOUS step (its last stores, dq_T, were issued by the I/O threads after B11)
-    if (sig_prev >= 0 && ioT) __threadfence();
     __syncthreads();
-    if (sig_prev >= 0 && tid == 0) atomicAdd(p.progress + sig_prev, 1u);
     GSCAN3_STAMP(3);
     // I/O warps: dgates of this step out (da_s is final and untouched until the next cell backward), the saved
     // activations of the next step (t - 1) in: asynchronous copies into the other staging buffer, awaited two barriers later
@@ -615,15 +612,21 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
       if (mg == 0) dqT_s[an * kVs + ah] = dq;
     }
     __syncthreads();
-    // dq_T is the last global store of the step.  "Rows t >= t_signal are complete" is published at the first block
-    // barrier of the NEXT step (fence by the I/O threads, which issued every store, before it; one add per CTA after
-    // it), or after the loop for a signal at t = 0
+    // dq_T is the last global store of the step, and every store of the step was issued by an I/O thread: "rows
+    // t >= t_signal are complete" is published right here by the I/O warps alone - fence by the writers, a barrier among
+    // the 64 I/O threads (named barrier 1), one add per CTA.  (At the first block barrier of the next step, as in round 1,
+    // the fence sat in the instruction stream of the compute warps and pinned their memory operations, taken or not.)
     io_store(dqT_s, kVs, 5, p.dqT, row0, kH, false);
-    sig_prev = -1;
-    if (p.progress != nullptr) {
+    if (p.progress != nullptr && ioT) {
+      int sig = -1;
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (k < p.n_signals && t == p.t_signal[k]) sig_prev = k;
+        if (k < p.n_signals && t == p.t_signal[k]) sig = k;
+      if (sig >= 0) {
+        __threadfence();
+        asm volatile("bar.sync 1, %0;" ::"n"(kIoThreads) : "memory");
+        if (io == 0) atomicAdd(p.progress + sig, 1u);
+      }
     }
     GSCAN3_STAMP(14);
     // ---- B12: last piece of dh, W_qT^T dq_T, added to the earlier pieces and reduce-scattered (X_d) ------------------------------
@@ -642,11 +645,6 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_bw
   }
 
   // ---- epilogue -------------------------------------------------------------------------------------------
-  if (sig_prev >= 0) {   // a signal at the very last step (not used by the host: cut points are > 0)
-    if (ioT) __threadfence();
-    __syncthreads();
-    if (tid == 0) atomicAdd(p.progress + sig_prev, 1u);
-  }
   mbar_wait(bar0 + 8u * 4, (uint32_t)((it - 1) & 1));
   if (cn_ok) {
     float dh = dh_extra;

@@ -74,18 +74,38 @@ void chain_mark(const char* name, cudaStream_t st) {
   cudaEventRecord(e, st);
   chain_marks().push_back({name, e});
 }
+// GSCAN_CHAIN_TIMES=2: deferred - the marks of a call are printed by the NEXT call with the same title, one step later,
+// so that the host stays ahead of the GPU (a report that synchronises exposes the host's launch cadence at the start of
+// every pass, which the pipelined loop does not have)
+void chain_print(const char* title, std::vector<ChainMark>& marks) {
+  fprintf(stderr, "[chain] %s:", title);
+  for (auto& m : marks) {
+    float ms = 0.f;
+    cudaEventSynchronize(m.ev);
+    cudaEventElapsedTime(&ms, marks[0].ev, m.ev);
+    fprintf(stderr, " %s=%.0f", m.name, ms * 1000.f);
+  }
+  fprintf(stderr, "\n");
+  for (auto& m : marks) cudaEventDestroy(m.ev);
+  marks.clear();
+}
 void chain_report(const char* title) {
   if (!chain_times_on() || chain_marks().empty()) return;
+  static const bool deferred = atoi(getenv("GSCAN_CHAIN_TIMES")) == 2;
+  if (deferred) {
+    static std::vector<std::pair<std::string, std::vector<ChainMark>>> pending;
+    for (auto& pr : pending)
+      if (pr.first == title) {
+        if (!pr.second.empty()) chain_print(title, pr.second);
+        pr.second.swap(chain_marks());
+        return;
+      }
+    pending.emplace_back(title, std::vector<ChainMark>());
+    pending.back().second.swap(chain_marks());
+    return;
+  }
   cudaDeviceSynchronize();
-  fprintf(stderr, "[chain] %s:", title);
-  for (auto& m : chain_marks()) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, chain_marks()[0].ev, m.ev);
-    fprintf(stderr, " %s=%.0f", m.name, ms * 1000.f);
-    }
-  fprintf(stderr, "\n");
-  for (auto& m : chain_marks()) cudaEventDestroy(m.ev);
-  chain_marks().clear();
+  chain_print(title, chain_marks());
 }
 
 // ---- internal fork / join ------------------------------------------------------------------

@@ -304,14 +304,15 @@ class NLLLoss(torch.autograd.Function):
     (gscan_nll_forward / _backward)."""
 
     @staticmethod
-    def forward(ctx, logp, targets, pad_idx, shift, clone_out=True):
+    def forward(ctx, logp, targets, pad_idx, shift, clone_out=True, out=None):
         lib = _lib.load()
         _require_cuda(logp, targets)
         ctx.set_materialize_grads(False)
         logp = logp.contiguous().float()
         targets = targets.contiguous()
         B, T, V = logp.shape
-        out = torch.empty(68, dtype=torch.float32, device=logp.device)   # GSCAN_NLL_OUT_FLOATS: [mean, count | scratch]
+        if out is None:
+            out = torch.empty(68, dtype=torch.float32, device=logp.device)   # GSCAN_NLL_OUT_FLOATS: [mean, count | scratch]
         _lib.check(lib.gscan_nll_forward(_ptr(logp), _ptr(targets), B, T, V, int(pad_idx), int(shift), _ptr(out),
                                          _stream(logp.device)), "gscan_nll_forward")
         _call_counts["other"] += 1
@@ -328,7 +329,7 @@ class NLLLoss(torch.autograd.Function):
     def backward(ctx, d_loss, _d_count):
         lib = _lib.load()
         if d_loss is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         targets, out = ctx.saved_tensors
         B, T, V, pad_idx, shift = ctx.meta
         d_loss = d_loss.contiguous().float().reshape(1)
@@ -336,21 +337,25 @@ class NLLLoss(torch.autograd.Function):
         _lib.check(lib.gscan_nll_backward(_ptr(targets), B, T, V, pad_idx, shift, _ptr(out), _ptr(d_loss), _ptr(d_logp),
                                           _stream(out.device)), "gscan_nll_backward")
         _call_counts["other"] += 1
-        return d_logp, None, None, None, None
+        return d_logp, None, None, None, None, None
 
 
-def nll_grad_from_targets(targets: torch.Tensor, V: int, pad_idx: int, shift: int, sum_form: bool):
+def nll_grad_from_targets(targets: torch.Tensor, V: int, pad_idx: int, shift: int, sum_form: bool,
+                          d_logp: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
     """d(loss)/d(logp) of the mean (``sum_form`` False) or the sum of the NLL terms ``NLLLoss`` scores, formed from the
     targets alone (gscan_nll_count + gscan_nll_backward) - bit-identical to what ``NLLLoss.backward`` returns for
-    ``loss = mean`` resp. ``loss = mean * count``.  Returns (d_logp [B, T, V], result buffer with the count at [1])."""
+    ``loss = mean`` resp. ``loss = mean * count``.  Returns (d_logp [B, T, V], result buffer with the count at [1]);
+    ``d_logp`` / ``out`` may be handed in (buffers a caller reuses from step to step)."""
     lib = _lib.load()
     _require_cuda(targets)
     targets = targets.contiguous()
     B, T = targets.shape
     dev = targets.device
-    out = torch.empty(68, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(68, dtype=torch.float32, device=dev)
     _lib.check(lib.gscan_nll_count(_ptr(targets), B, T, int(pad_idx), int(shift), _ptr(out), _stream(dev)), "gscan_nll_count")
-    d_logp = torch.empty(B, T, V, dtype=torch.float32, device=dev)
+    if d_logp is None or d_logp.shape != (B, T, V):
+        d_logp = torch.empty(B, T, V, dtype=torch.float32, device=dev)
     d_loss = out[1:2] if sum_form else _ones1(dev)     # d loss / d mean = count, resp. 1
     _lib.check(lib.gscan_nll_backward(_ptr(targets), B, T, V, int(pad_idx), int(shift), _ptr(out), _ptr(d_loss), _ptr(d_logp),
                                       _stream(dev)), "gscan_nll_backward")

@@ -45,6 +45,8 @@ class FusedTrainer:
         # pass writes into it (ops.set_flat_grad_target), the data-parallel all-reduce sums all of it at once
         self.flat_grad = torch.zeros(n + dp.COUNT_SLOTS, dtype=torch.float32, device=dev)
         self._side_stream = torch.cuda.Stream(device=dev)   # zeroing, early loss gradient, loss value (train_step)
+        self._d_logp = None
+        self._count_out = None
         self._one = torch.ones((), dtype=torch.float32, device=dev)   # d loss / d loss, without a fill kernel per step
         # re-seat every parameter as a view into the flat buffer (identity of the nn.Parameter kept)
         with torch.no_grad():
@@ -110,12 +112,19 @@ class FusedTrainer:
         side = self._side_stream
         early_grad = not use_aux
         side.wait_stream(main)           # the previous step's Adam has read the gradient buffer; the targets are there
+        # (nothing is ALLOCATED under the second stream: blocks that cross streams come back to the caching allocator
+        #  late, and the cudaMalloc calls that then fill the gap showed up as 40-80 ms stalls every few dozen steps)
+        if early_grad:
+            V = int(model._static_cfg["V"])
+            if self._d_logp is None or self._d_logp.shape != (targets.shape[0], targets.shape[1], V):
+                self._d_logp = torch.empty(targets.shape[0], targets.shape[1], V, dtype=torch.float32, device=targets.device)
+                self._count_out = torch.empty(68, dtype=torch.float32, device=targets.device)
+            loss_out = torch.empty(68, dtype=torch.float32, device=targets.device)   # fresh: the caller may keep the loss
         with torch.cuda.stream(side):
             self.flat_grad[:n].zero_()
             if early_grad:
-                d_logp, _ = ops.nll_grad_from_targets(targets, int(model._static_cfg["V"]), model.target_pad_idx, 1,
-                                                      sum_form=self.distributed)
-                d_logp.record_stream(main)
+                d_logp, _ = ops.nll_grad_from_targets(targets, V, model.target_pad_idx, 1, sum_form=self.distributed,
+                                                      d_logp=self._d_logp, out=self._count_out)
         logp, aux = model(commands_input=commands, commands_lengths=commands_lengths, situations_input=situations,
                           target_batch=targets, target_lengths=target_lengths)
         main.wait_stream(side)
@@ -129,10 +138,8 @@ class FusedTrainer:
                 ops.set_flat_grad_target(None)
             with torch.cuda.stream(side), torch.no_grad():
                 side.wait_event(fwd_done)
-                logp.record_stream(side)
-                nll, n_tok = ops.NLLLoss.apply(logp.detach(), targets, model.target_pad_idx, 1, False)
-                loss = nll * n_tok if self.distributed else nll
-                loss.record_stream(main)
+                nll, n_tok = ops.NLLLoss.apply(logp.detach(), targets, model.target_pad_idx, 1, False, loss_out)
+            loss = None      # formed on the caller's stream once it has waited for the second one (below)
         else:
             nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1, False)
             aux_mean = model.get_auxiliary_loss(aux, target_positions)
@@ -165,6 +172,8 @@ class FusedTrainer:
         ops.adam_step(self.flat_param, flat_grad[:n], self.exp_avg, self.exp_avg_sq, lr, self.betas[0], self.betas[1],
                       self.eps, self.step_count, grad_denom=denom)
         main.wait_stream(side)           # the loss value (and nothing else) comes from the second stream
+        if loss is None:
+            loss = nll * n_tok if self.distributed else nll
         model.update_state(is_best=False)
         self.last_logp, self.last_aux = logp.detach(), aux
         self.last_flat_grad = flat_grad

@@ -1,0 +1,165 @@
+"""Turn the raw outputs of tools/r02_final.sh (gpurun_out/r02f_*) into the committed evidence under profiles/r02_*.
+usage: python tools/r02_collect.py   (in the build container, after the gpurun call; needs ncu for the .ncu-rep exports)"""
+import csv
+import collections
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+O = os.path.join(ROOT, "gpurun_out")
+P = os.path.join(ROOT, "profiles")
+
+
+def sh(cmd, **kw):
+    return subprocess.run(cmd, shell=True, capture_output=True, text=True, cwd=ROOT, **kw).stdout
+
+
+def copy(src, dst):
+    if os.path.exists(os.path.join(O, src)):
+        shutil.copy(os.path.join(O, src), os.path.join(P, dst))
+        return True
+    print("missing", src)
+    return False
+
+
+def last_json_line(path):
+    for line in reversed(open(path).read().strip().splitlines()):
+        line = line.strip()
+        if line.startswith("{"):
+            return json.loads(line)
+    return None
+
+
+# ---- bench lines (one JSON line each, pretty-printed copies would not be "the line": kept verbatim) ------------------
+for src, dst in (("r02f_bench.json", "r02_bench.json"), ("r02f_bench_comp_aux.json", "r02_bench_comp_aux.json"),
+                 ("r02f_bench_tlen.json", "r02_bench_tlen.json"), ("r02f_bench_reference.json", "r02_bench_reference.json"),
+                 ("r02f_tests.log", "r02_gpu_tests.log"), ("r02f_margins.json", "r02_error_margins.json"),
+                 ("r02f_cnn.json", "r02_cnn_density.json"), ("r02f_launches.csv", "r02_launches.csv"),
+                 ("r02f_step_trace.md", "r02_step_trace.md")):
+    copy(src, dst)
+
+# ---- micro-benchmarks ----------------------------------------------------------------------------------------------------
+if os.path.exists(os.path.join(O, "r02f_ubench.txt")):
+    with open(os.path.join(P, "r02_ubench.md"), "w") as f:
+        f.write("# Round 2 micro-benchmarks on one B200 (tools/r02_final.sh; sources under tools/, binaries built by the "
+                "nvcc line in each source's header)\n\n```\n")
+        f.write(open(os.path.join(O, "r02f_ubench.txt")).read())
+        f.write("```\n\n## tools/tc_gemm_dev.cu: the tcgen05 3xTF32 GEMM against fp64 and against the mma.sync kernel, shapes of the step\n\n```\n")
+        if os.path.exists(os.path.join(O, "r02f_tc_gemm_dev.txt")):
+            f.write(open(os.path.join(O, "r02f_tc_gemm_dev.txt")).read())
+        f.write("```\n")
+
+# ---- per-warp timelines of the sweeps -------------------------------------------------------------------------------------
+tl = []
+for side in ("fwd", "bwd"):
+    b = os.path.join(O, "r02f_tl.%s.bin" % side)
+    if os.path.exists(b):
+        tl.append("## %s sweep: when each warp of CTA 0 reached each stamp (average cycles after the step's first stamp)\n\n```\n%s```\n"
+                  % ("Forward" if side == "fwd" else "Backward", sh("python tools/timeline_table.py %s" % b)))
+if tl:
+    err = open(os.path.join(O, "r02f_timeline.err")).read() if os.path.exists(os.path.join(O, "r02f_timeline.err")) else ""
+    with open(os.path.join(P, "r02_timeline.md"), "w") as f:
+        f.write("# Round 2: per-warp phase timeline of the shipping sweeps (instrumented instantiations, GSCAN_TIMELINE)\n\n"
+                "`GSCAN_TIMELINE=<prefix> python bench.py --steps 2 ...` (tools/r02_final.sh); stamps are `clock64` of lane 0 of every "
+                "warp of CTA 0 (template flag TL: the production kernels carry none of it).  Stamp numbers: GSCAN3_STAMP(k) in "
+                "csrc/decoder_v3.cuh / decoder_v3_bwd.cuh.\n\n```\n")
+        f.write("\n".join(l for l in err.splitlines() if l.startswith("[gscan]")) + "\n```\n\n")
+        f.write("\n".join(tl))
+
+# ---- pipelined chain times + host probe, appended to the step trace --------------------------------------------------------
+st = os.path.join(P, "r02_step_trace.md")
+if os.path.exists(st):
+    with open(st, "a") as f:
+        ce = os.path.join(O, "r02f_chain.err")
+        if os.path.exists(ce):
+            lines = [l for l in open(ce).read().splitlines() if l.startswith("[chain]")]
+            f.write("\n## Chain marks of a pipelined step (GSCAN_CHAIN_TIMES=2: read one step late, the host stays ahead), us\n\n```\n")
+            f.write("\n".join(lines[-4:]) + "\n```\n")
+        hp = os.path.join(O, "r02f_host_probe.txt")
+        if os.path.exists(hp):
+            f.write("\n## Host side (tools/host_sync_probe.py): time per train_step call without synchronisation\n\n```\n")
+            f.write("\n".join(open(hp).read().splitlines()[-3:]) + "\n```\n")
+
+# ---- ncu: sweeps (json + md through the existing tool), Z kernel, per-kernel table of the launch list ---------------------------
+rep = os.path.join(O, "r02f_sweeps.ncu-rep")
+if os.path.exists(rep):
+    raw = os.path.join(O, "r02f_raw.csv")
+    open(raw, "w").write(sh("ncu -i %s --page raw --csv" % rep))
+    print(sh("python tools/ncu_sweeps_summary.py %s" % raw))
+    src = os.path.join(O, "r02f_source.csv")
+    open(src, "w").write(sh("ncu -i %s --page source --csv" % rep))
+    with open(os.path.join(P, "r02_ncu_phases.md"), "w") as f:
+        f.write("# Round 2: the SASS stream of the shipping sweeps cut at every barrier / mbarrier wait of the time loop "
+                "(tools/ncu_phases.py on the source page of the same capture)\n\n")
+        for k in ("dec_fwd_v3", "dec_bwd_v3"):
+            f.write("```\n" + sh("python tools/ncu_phases.py %s %s" % (src, k)) + "```\n\n")
+
+zrep = os.path.join(O, "r02f_zm.ncu-rep")
+if os.path.exists(zrep):
+    rows = list(csv.reader(sh("ncu -i %s --page details --csv" % zrep).splitlines()))
+    h = rows[0]
+    mi, vi, ui = h.index("Metric Name"), h.index("Metric Value"), h.index("Metric Unit")
+    want = ["Duration", "Registers Per Thread", "Dynamic Shared Memory Per Block", "Waves Per SM", "Achieved Occupancy",
+            "Executed Ipc Active", "Issue Slots Busy", "No Eligible", "Executed Instructions", "DRAM Throughput",
+            "Memory Throughput", "L1/TEX Hit Rate", "L2 Hit Rate", "Compute (SM) Throughput"]
+    with open(os.path.join(P, "r02_ncu_value_z.md"), "w") as f:
+        f.write("# Round 2: `ncu --set full` of the tensor-core value-path kernel (`attn_value_zm_kernel<3>`, one launch of a training step)\n\n"
+                "| metric | value |\n|---|---|\n")
+        for r in rows[1:]:
+            if r[mi] in want:
+                f.write("| %s | %s %s |\n" % (r[mi], r[vi], r[ui]))
+        f.write("\nThe FFMA2 kernel it replaces (`attn_value_z_kernel`, profiles/r01_v5_ncu_new_kernels.md): 64 us, 29.0 M warp "
+                "instructions (14.3 M FFMA2), IPC 2.08 - bound by issue.  This one issues 2.2 M mma.sync + ~11 M others; what is left "
+                "is the strided gather of X (1 KB row segments 320 KB apart) at 1.35 waves of 3 CTAs per SM.\n")
+
+lc = os.path.join(P, "r02_launches.csv")
+bj = os.path.join(P, "r02_bench.json")
+if os.path.exists(lc) and os.path.exists(bj):
+    rows = list(csv.reader(open(lc, errors="replace")))
+    hdr = next(r for r in rows if "Kernel Name" in r)
+    out = [dict(zip(hdr, r)) for r in rows if len(r) == len(hdr) and r[0] != "ID"]
+    ad = [i for i, d in enumerate(out) if "adam_kernel" in d["Kernel Name"]]
+    if len(ad) >= 2:
+        step = out[ad[-2] + 1:ad[-1] + 1]
+        agg = collections.OrderedDict()
+        for d in step:
+            n = re.sub(r"\(.*", "", d["Kernel Name"])
+            a = agg.setdefault(n, [0, 0.0])
+            a[0] += 1
+            a[1] += float(d["Metric Value"].replace(",", "")) / 1e3
+        tot = sum(v[1] for v in agg.values())
+        b = last_json_line(bj)
+        with open(os.path.join(P, "r02_summary.md"), "w") as f:
+            f.write("# Round 2: one training step, kernel by kernel\n\n"
+                    "Launch list: `ncu --metrics gpu__time_duration.sum --clock-control none` over `python bench.py --steps 2 --warmup 3` "
+                    "(tools/r02_final.sh; `profiles/r02_launches.csv`).  Times under ncu are serialised and cold-cache: the SHARE of a kernel "
+                    "is what counts; the live numbers are in the bench line (`profiles/r02_bench.json`: %.0f ex/s, %.4f ms/step, e2e %.0f ex/s, "
+                    "%d launches per step) and the concurrent picture in `profiles/r02_step_trace.md`.\n\n"
+                    % (b["value"], b["ms_per_step"], b["e2e"]["value"], b.get("gpu_launches", 0) // max(1, b["steps"])))
+            f.write("| us (sum, serialised) | launches | share | kernel |\n|---:|---:|---:|---|\n")
+            for n, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write("| %.1f | %d | %.1f %% | %s |\n" % (us, c, 100 * us / tot, n))
+            f.write("| **%.1f** | **%d** | | one step, %d of them ours |\n" % (tot, sum(v[0] for v in agg.values()),
+                                                                             sum(v[0] for k, v in agg.items() if "gscan" in k)))
+
+# ---- sanitizer ----------------------------------------------------------------------------------------------------------------
+san = []
+for tool in ("memcheck", "synccheck", "racecheck"):
+    pth = os.path.join(O, "r02f_%s.log" % tool)
+    if os.path.exists(pth):
+        txt = open(pth).read()
+        errs = re.findall(r"ERROR SUMMARY: (\d+) error", txt)
+        hz = re.findall(r"RACECHECK SUMMARY: (\d+) hazard", txt)
+        tail = [l for l in txt.strip().splitlines() if "passed" in l or "failed" in l][-1:]
+        san.append("| %s | %s | %s |" % (tool, ", ".join(errs + [x + " hazards" for x in hz]) or "-", tail[0].strip() if tail else "?"))
+if san:
+    with open(os.path.join(P, "r02_sanitizer.md"), "w") as f:
+        f.write("# Round 2: compute-sanitizer passes over the shipping kernels (tools/r02_final.sh)\n\n"
+                "Small cases of the parity suite (training step with the auxiliary task, greedy decoding, encode / step API, dense "
+                "situations) under each tool; cluster sweeps, st.async exchanges, named barriers and the cp.async I/O warps included.\n\n"
+                "| tool | errors reported | pytest |\n|---|---|---|\n" + "\n".join(san) + "\n")
+print("done")
