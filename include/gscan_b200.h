@@ -241,6 +241,22 @@ int gscan_forward_rng(const gscan_dims* d, const float* const* params,
                       const int64_t* commands, const int32_t* cmd_len, const float* situations,
                       const int64_t* targets, const gscan_dropout* rng,
                       float* workspace, size_t workspace_floats, float* logp, float* aux_logp, void* stream);
+/*
+ * Forward pass of a TRAINING step whose loss gradient with respect to the log-probabilities is known in advance (for the
+ * reference's loss - NLLLoss of the shifted targets, train.py:102-107 - it depends on the targets only: gscan_nll_count +
+ * gscan_nll_backward).  As gscan_forward (masks) / gscan_forward_rng (rng != NULL), and the output-head backward pass -
+ * log-softmax backward, hidden_to_output and output_to_hidden, what model.py:188 and seq2seq_model.py:378-380 leave to
+ * autograd - runs inside this call, most of it beside the decoder sweep; the gscan_backward[_rng] call that follows on
+ * the same workspace with the SAME d_logp pointer (contents unchanged) then starts with the reverse-time sweep.  A
+ * backward call with another d_logp recomputes that stage: results never depend on which path ran.
+ * d_logp_ready: NULL, or a cudaEvent_t recorded after the work that produces d_logp (it may still be running on another
+ * stream when this call is made; only the head-backward kernels wait for it).
+ */
+int gscan_forward_train(const gscan_dims* d, const float* const* params,
+                        const int64_t* commands, const int32_t* cmd_len, const float* situations,
+                        const int64_t* targets, const float* drop_cnn, const float* drop_enc, const float* drop_dec,
+                        const gscan_dropout* rng, float* workspace, size_t workspace_floats, float* logp,
+                        float* aux_logp, const float* d_logp /* [B,Tt,V] */, void* d_logp_ready, void* stream);
 int gscan_backward_rng(const gscan_dims* d, const float* const* params,
                        const int64_t* commands, const int32_t* cmd_len, const float* situations,
                        const int64_t* targets, const gscan_dropout* rng,

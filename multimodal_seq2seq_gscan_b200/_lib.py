@@ -58,6 +58,9 @@ SIGNATURES = {
                                  POINTER(ParamArray), c_void_p]),
     "gscan_forward_rng": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p,
                                     POINTER(Dropout), c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "gscan_forward_train": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, POINTER(Dropout), c_void_p, c_size_t, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "gscan_backward_rng": (c_int32, [POINTER(Dims), POINTER(ParamArray), c_void_p, c_void_p, c_void_p, c_void_p,
                                      POINTER(Dropout), c_void_p, c_size_t, c_void_p, c_void_p, POINTER(ParamArray),
                                      c_void_p]),

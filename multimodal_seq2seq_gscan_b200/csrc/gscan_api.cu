@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -169,6 +171,7 @@ struct Layout {
   size_t U, Xe, Cs, gates, alpha, beta, Qp, qT, qV, beta_sum, aux_logp, pre, logp;
   size_t tag;                  // which decoder sweep the forward call ran (checked by the v3 backward kernel)
   size_t progress_f;           // progress words of the forward sweep (output head in its shadow)
+  size_t dWh2o;                // hidden_to_output weight gradient formed inside the forward call (gscan_forward_train)
   // backward scratch
   size_t dlogits, dpre, dU, dgates, dd, dqV, dqT, dKT, dKV, dh0, dbeta_aux, dfeat, dconv, dWt_cnn;
   size_t denc_out, dh_enc, dpre0, dga[2], hprev[2], denc_x, dvec;
@@ -220,6 +223,7 @@ Layout make_layout(const gscan_dims& d, bool with_backward) {
   L.logp = L.take(B * Tt * V);
   L.tag = L.take(4);
   L.progress_f = L.take(4);
+  L.dWh2o = L.take(V * H);
   if (with_backward) {
     L.dlogits = L.take(Tt * B * V);
     L.dpre = L.take(Tt * B * H);
@@ -923,7 +927,27 @@ DropSrc make_drop(const float* mask, const gscan_dropout* rng, int which) {
 
 int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
                  const float* situations, const int64_t* targets, DropSrc drop_cnn, DropSrc drop_enc, DropSrc drop_dec,
-                 float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream);
+                 float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream,
+                 const float* d_logp_early = nullptr, cudaEvent_t d_logp_ready = nullptr);
+
+// gscan_forward_train: which workspaces hold an output-head backward pass already (dpre, dU, dW_h2o formed inside the
+// forward call from a d_logp known in advance), and for which d_logp pointer.  The backward call on the same workspace
+// with the same pointer skips that stage; any other d_logp recomputes it.
+std::mutex& early_head_mutex() { static std::mutex m; return m; }
+std::map<const float*, const float*>& early_head_map() { static std::map<const float*, const float*> m; return m; }
+void early_head_set(const float* ws, const float* d_logp) {
+  std::lock_guard<std::mutex> g(early_head_mutex());
+  if (d_logp) early_head_map()[ws] = d_logp;
+  else early_head_map().erase(ws);
+}
+bool early_head_take(const float* ws, const float* d_logp) {
+  std::lock_guard<std::mutex> g(early_head_mutex());
+  auto it = early_head_map().find(ws);
+  if (it == early_head_map().end()) return false;
+  const bool same = it->second == d_logp;
+  early_head_map().erase(it);
+  return same;
+}
 int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
                   const float* situations, const int64_t* targets, DropSrc drop_cnn, DropSrc drop_enc, DropSrc drop_dec,
                   float* ws, size_t ws_floats, const float* d_logp, const float* d_aux_logp, float* const* G, void* stream);
@@ -1008,6 +1032,15 @@ int gscan_forward_rng(const gscan_dims* d, const float* const* P, const int64_t*
                       make_drop(nullptr, rng, 2), ws, ws_floats, logp, aux_logp, stream);
 }
 
+int gscan_forward_train(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
+                        const float* situations, const int64_t* targets, const float* drop_cnn, const float* drop_enc,
+                        const float* drop_dec, const gscan_dropout* rng, float* ws, size_t ws_floats, float* logp,
+                        float* aux_logp, const float* d_logp, void* d_logp_ready, void* stream) {
+  if (!d_logp) return GSCAN_E_BADARG;
+  return forward_impl(d, P, commands, cmd_len, situations, targets, make_drop(drop_cnn, rng, 0), make_drop(drop_enc, rng, 1),
+                      make_drop(drop_dec, rng, 2), ws, ws_floats, logp, aux_logp, stream, d_logp, (cudaEvent_t)d_logp_ready);
+}
+
 int gscan_backward_rng(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
                        const float* situations, const int64_t* targets, const gscan_dropout* rng, float* ws,
                        size_t ws_floats, const float* d_logp, const float* d_aux_logp, float* const* G, void* stream) {
@@ -1033,7 +1066,8 @@ namespace {
 
 int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* commands, const int32_t* cmd_len,
                  const float* situations, const int64_t* targets, DropSrc drop_cnn, DropSrc drop_enc, DropSrc drop_dec,
-                 float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream) {
+                 float* ws, size_t ws_floats, float* logp, float* aux_logp, void* stream,
+                 const float* d_logp_early, cudaEvent_t d_logp_ready) {
   TRY(check_common(d, P));
   if (!commands || !cmd_len || !situations || !targets || !ws || !logp) return GSCAN_E_BADARG;
   if (d->auxiliary_task && !aux_logp) return GSCAN_E_BADARG;
@@ -1048,6 +1082,10 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   prof_mark(0, st);
   chain_mark("fwd_start", st);
   TRYCUDA(cudaMemsetAsync(ws + L.progress_f, 0, 4 * sizeof(unsigned int), st));   // progress words of the sweep (far ahead of it)
+  // gscan_forward_train: the output-head backward runs inside this call (fused kernel only: V <= kHeadMaxV, H <= 128)
+  early_head_set(ws, nullptr);
+  const bool early_head = d_logp_early != nullptr && V <= kHeadMaxV && H <= 128 && getenv("GSCAN_HEAD_UNFUSED") == nullptr;
+  if (early_head) TRYCUDA(cudaMemsetAsync(ws + L.dWh2o, 0, sizeof(float) * (size_t)V * H, st));
   // Three chains before the sweep: the command encoder (a long chain of small kernels: high-priority helper stream 1,
   // issued first), the decoder prelude (depends on targets and weights only; one big GEMM, capped: high-priority
   // helper stream 0) and the situation CNN (wide kernels of small CTAs that co-reside with the GEMM's: the caller's
@@ -1132,15 +1170,34 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     const size_t head_smem_l = keep_off_sweep_sms && head_smem < 80 * 1024 ? (size_t)80 * 1024 : head_smem;
     TRY(linear(U1 + (size_t)r0 * 4 * H, 4 * H, P[GSCAN_P_O2H_W], 4 * H, ws + L.pre + (size_t)r0 * H, H, (int)(r1 - r0), H,
                4 * H, nullptr, nullptr, 0, s_));
-    const int blocks = min(ceil_div((int)(r1 - r0), 8), 8 * num_sms());
+    // a shadow launch fits two CTAs on an idle SM (the shared-memory request above): 1024 threads each for full occupancy
+    const int hthreads = keep_off_sweep_sms ? 1024 : 256;
+    const int blocks = min(ceil_div((int)(r1 - r0), hthreads / 32), 8 * num_sms());
     // (the caller's copy of the log-probabilities is written here too: no copy kernel between the head and the loss)
-    out_logsoftmax_kernel<<<blocks, 256, head_smem_l, s_>>>(ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.logp, nullptr,
+    out_logsoftmax_kernel<<<blocks, hthreads, head_smem_l, s_>>>(ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.logp, nullptr,
                                                             r0, r1, logp);
     GSCAN_CHECK_LAUNCH();
     return 0;
   };
   int head_t0 = 0;               // first step whose output head is still to do after the sweep
   bool fwd_shadow_used = false;
+  // output-head backward of the steps [t0, t1) from a d_logp known in advance: log-softmax backward, dpre and the
+  // hidden_to_output weight gradient (into the workspace: the caller's gradient buffer is not known here) in one pass
+  // over the rows, then dU = dpre . W_o2h for them
+  const size_t hb_smem = 2 * sizeof(float) * (size_t)V * H;
+  if (early_head) TRY(set_smem(head_bwd_fused_kernel, hb_smem > 80 * 1024 ? hb_smem : (size_t)80 * 1024));
+  auto head_bwd_rows = [&](int t0, int t1, cudaStream_t s_, bool keep_off_sweep_sms) -> int {
+    const long r0 = (long)t0 * B, r1 = (long)t1 * B;
+    if (r1 <= r0) return 0;
+    const size_t sm_l = keep_off_sweep_sms && hb_smem < 80 * 1024 ? (size_t)80 * 1024 : hb_smem;
+    head_bwd_fused_kernel<<<min(ceil_div((int)(r1 - r0), 8), 2 * num_sms()), 256, sm_l, s_>>>(
+        d_logp_early, ws + L.logp, ws + L.pre, P[GSCAN_P_H2O_W], H, V, B, Tt, ws + L.dpre, ws + L.dWh2o, r0, r1);
+    GSCAN_CHECK_LAUNCH();
+    TRY(matmul_nn(ws + L.dpre + (size_t)r0 * H, H, P[GSCAN_P_O2H_W], 4 * H, ws + L.dU + (size_t)r0 * 4 * H, 4 * H,
+                  (int)(r1 - r0), 4 * H, H, 0, s_));
+    return 0;
+  };
+  int head_bwd_t0 = 0;           // first step whose output-head backward is still to do after the sweep
   if (v3_shape_ok(*d)) {
     v3::DecFwd3P p3{};
     p3.B = B; p3.T = Tt; p3.Ti = d->Ti;
@@ -1158,7 +1215,7 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
     int nf = 0;
     {
       const char* spec = getenv("GSCAN_FWD_SHADOW_CUTS");
-      if (!spec) spec = "25,50,72,90";
+      if (!spec) spec = "20,44,68,92";
       int prev = 0;
       for (const char* q = spec; *q && nf < 4;) {
         const int pct = atoi(q);
@@ -1197,8 +1254,17 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
           break;
         }
         TRY(head_rows(k == 0 ? 0 : f_cut[k - 1], f_cut[k], sh, true));
+        // ... and, with d_logp known in advance, their backward pass too - for the first chunks only: the 23 idle SMs
+        // cannot take all of it before the sweep ends (GSCAN_FWD_SHADOW_BWD_CHUNKS)
+        static const int bwd_chunks = env_int("GSCAN_FWD_SHADOW_BWD_CHUNKS", 3);   // of 4: the last one would end after the sweep
+        if (early_head && k < bwd_chunks) {
+          if (k == 0 && d_logp_ready) TRYCUDA(cudaStreamWaitEvent(sh, d_logp_ready, 0));
+          TRY(head_bwd_rows(k == 0 ? 0 : f_cut[k - 1], f_cut[k], sh, true));
+          head_bwd_t0 = f_cut[k];
+        }
       }
       if (fshadow) head_t0 = f_cut[nf - 1];
+      else head_bwd_t0 = 0;
     }
     fwd_shadow_used = fshadow;
   }
@@ -1222,6 +1288,11 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   // way the backward pass does it, were a net loss: DESIGN.md 4.5 - and the signal code alone cost the sweep 33 us.)
   TRY(head_rows(head_t0, Tt, st));
   if (fwd_shadow_used) TRY(join_side(S, 2, st));
+  if (early_head) {
+    if (d_logp_ready) TRYCUDA(cudaStreamWaitEvent(st, d_logp_ready, 0));
+    TRY(head_bwd_rows(head_bwd_t0, Tt, st, false));
+    early_head_set(ws, d_logp_early);
+  }
   if (d->auxiliary_task) {
     row_logsoftmax_kernel<<<ceil_div(B, 8), 256, 0, st>>>(ws + L.beta_sum, M, B, ws + L.aux_logp);
     GSCAN_CHECK_LAUNCH();
@@ -1276,7 +1347,11 @@ int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* com
   // B1: log-softmax backward, hidden_to_output
   prof_mark(5, st);
   const bool head_fused = V <= kHeadMaxV && H <= 128 && getenv("GSCAN_HEAD_UNFUSED") == nullptr;
-  if (head_fused) {
+  // gscan_forward_train has done B1 and B2 already for this d_logp: only the weight gradient has to reach the caller
+  const bool head_done = early_head_take(ws, d_logp) && head_fused;
+  if (head_done) {
+    TRYCUDA(cudaMemcpyAsync(G[GSCAN_P_H2O_W], ws + L.dWh2o, sizeof(float) * (size_t)V * H, cudaMemcpyDeviceToDevice, st));
+  } else if (head_fused) {
     // log-softmax backward, dpre and the hidden_to_output weight gradient in one pass over the rows
     TRYCUDA(cudaMemsetAsync(G[GSCAN_P_H2O_W], 0, sizeof(float) * (size_t)V * H, st));
     head_bwd_fused_kernel<<<min(ceil_div(R, 8), 2 * sms), 256, 2 * sizeof(float) * (size_t)V * H, st>>>(
@@ -1291,7 +1366,7 @@ int backward_impl(const gscan_dims* d, const float* const* P, const int64_t* com
   // B2: output_to_hidden.  The two output-head weight gradients are not needed by the sweep: they are issued after
   // it, on helper stream 1 beside the other post-sweep chains.  (Running them on a helper stream BEFORE the sweep
   // delays the cluster launch of the sweep behind the persistent GEMM: measured 1.11 -> 1.45 ms for the sweep.)
-  TRY(matmul_nn(ws + L.dpre, H, P[GSCAN_P_O2H_W], 4 * H, ws + L.dU, 4 * H, R, 4 * H, H, 0, st));
+  if (!head_done) TRY(matmul_nn(ws + L.dpre, H, P[GSCAN_P_O2H_W], 4 * H, ws + L.dU, 4 * H, R, 4 * H, H, 0, st));
   // B3: auxiliary head
   const float* dbeta_aux = nullptr;
   if (d->auxiliary_task && d_aux_logp) {

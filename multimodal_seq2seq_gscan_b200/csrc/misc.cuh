@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const long long* __restr
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxVPerLane = 4;
 
-__global__ void __launch_bounds__(256) out_logsoftmax_kernel(const float* __restrict__ pre, const float* __restrict__ Wh2o,
+__global__ void __launch_bounds__(1024) out_logsoftmax_kernel(const float* __restrict__ pre, const float* __restrict__ Wh2o,
                                                              int H, int V, int B, int T, float* __restrict__ logp,
                                                              float* __restrict__ logits_out /* [R][V] or null */,
                                                              long row_begin = 0, long row_end = -1,
@@ -234,20 +234,20 @@ constexpr int kHeadMaxV = 16;
 __global__ void __launch_bounds__(256) head_bwd_fused_kernel(const float* __restrict__ dlogp, const float* __restrict__ logp,
                                                              const float* __restrict__ pre, const float* __restrict__ Wh2o,
                                                              int H, int V, int B, int T, float* __restrict__ dpre,
-                                                             float* __restrict__ dW) {
+                                                             float* __restrict__ dW, long row_begin = 0, long row_end = -1) {
   extern __shared__ __align__(16) float hb_s[];   // W [V][H] then dW accumulator [V][H]
   float* w_s = hb_s;
   float* acc_s = hb_s + V * H;
   for (int i = threadIdx.x; i < V * H; i += blockDim.x) { w_s[i] = __ldg(Wh2o + i); acc_s[i] = 0.f; }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long R = (long)B * T;
+  const long R = row_end >= 0 ? row_end : (long)B * T;   // rows [row_begin, R) of the time-major list
   float acc[kHeadMaxV][4];
 #pragma unroll
   for (int v = 0; v < kHeadMaxV; ++v)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[v][i] = 0.f;
-  for (long row = (long)blockIdx.x * (blockDim.x >> 5) + warp; row < R; row += (long)gridDim.x * (blockDim.x >> 5)) {
+  for (long row = row_begin + (long)blockIdx.x * (blockDim.x >> 5) + warp; row < R; row += (long)gridDim.x * (blockDim.x >> 5)) {
     const int t = row / B, b = row - (long)t * B;
     const long off = ((long)b * T + t) * V;
     const float dl = lane < V ? __ldg(dlogp + off + lane) : 0.f;

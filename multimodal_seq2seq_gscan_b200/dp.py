@@ -76,6 +76,16 @@ def shard_batch(batch: Sequence, rank: int, world: int, auxiliary_task: bool):
     return sub, global_counts
 
 
+def batch_const(targets: torch.Tensor) -> torch.Tensor:
+    """The number of examples of ``targets`` as a cached 1-element fp32 tensor on its device (no host-to-device copy
+    per step: such an assignment stalls the enqueueing thread until the stream drains)."""
+    key = (targets.device, int(targets.shape[0]), 1)
+    t = _BATCH_CONST.get(key)
+    if t is None:
+        t = _BATCH_CONST[key] = torch.full((1,), float(targets.shape[0]), dtype=torch.float32, device=targets.device)
+    return t
+
+
 def local_counts(targets: torch.Tensor, pad_idx: int) -> torch.Tensor:
     """[non-pad target tokens after the SOS column, examples] of this rank's shard, on the device of
     `targets` - exactly what NLLLoss(ignore_index) / the auxiliary NLLLoss divide by (model.py:100,59)."""

@@ -186,7 +186,17 @@ class ModelForward(torch.autograd.Function):
         aux = torch.empty(B, M, dtype=torch.float32, device=dev) if dims.auxiliary_task else None
         parr = _param_array([None if p is None else p.detach() for p in params])
         ctx.rng = masks if isinstance(masks, Dropout) else None
-        if ctx.rng is not None:
+        early = _take_early_dlogp(logp)
+        if early is not None:
+            # training step with d(loss)/d(logp) known in advance: the output-head backward runs inside the forward call
+            d_early, ready = early
+            rng = ctx.rng
+            if rng is not None:
+                masks = (None, None, None)
+            rc = lib.gscan_forward_train(dims, parr, _ptr(commands), _ptr(cmd_len_dev), _ptr(situations), _ptr(targets),
+                                         _ptr(masks[0]), _ptr(masks[1]), _ptr(masks[2]), rng, _ptr(ws), n_ws, _ptr(logp),
+                                         _ptr(aux), _ptr(d_early), ready, _stream(dev))
+        elif ctx.rng is not None:
             rc = lib.gscan_forward_rng(dims, parr, _ptr(commands), _ptr(cmd_len_dev), _ptr(situations), _ptr(targets),
                                        ctx.rng, _ptr(ws), n_ws, _ptr(logp), _ptr(aux), _stream(dev))
             masks = (None, None, None)
@@ -271,6 +281,30 @@ def set_flat_grad_target(buf: Optional[torch.Tensor], prezeroed: bool = False) -
     global _flat_grad_target, _flat_grad_prezeroed
     _flat_grad_target = buf
     _flat_grad_prezeroed = bool(prezeroed) and buf is not None
+
+
+_early_dlogp = None
+
+
+def set_early_dlogp(d_logp: Optional[torch.Tensor], ready_event: Optional["torch.cuda.Event"] = None) -> None:
+    """The NEXT ``ModelForward.forward`` is the forward pass of a training step whose d(loss)/d(logp) is ``d_logp``
+    ([B, Tt, V] fp32, contiguous; ``nll_grad_from_targets``): it goes through gscan_forward_train, which also runs the
+    output-head backward pass.  The backward call must then be given the SAME tensor (``torch.autograd.grad(...,
+    grad_outputs=[d_logp])``); anything else is correct too, the head is then recomputed.  ``ready_event``: recorded
+    after the work that fills ``d_logp`` when that work runs on another stream."""
+    global _early_dlogp
+    _early_dlogp = None if d_logp is None else (d_logp, ready_event)
+
+
+def _take_early_dlogp(logp: torch.Tensor):
+    global _early_dlogp
+    e, _early_dlogp = _early_dlogp, None
+    if e is None:
+        return None
+    d, ev = e
+    if d.shape != logp.shape or d.dtype != torch.float32 or d.device != logp.device or not d.is_contiguous():
+        return None
+    return d, (None if ev is None else ev.cuda_event)
 
 
 def _take_flat_grad_target(n_flat: int, device) -> Optional[torch.Tensor]:

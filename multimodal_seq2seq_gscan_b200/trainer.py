@@ -97,11 +97,11 @@ class FusedTrainer:
         n = self._n
         use_aux = bool(model.auxiliary_task and target_positions is not None and self.weight_target_loss != 0)
         counts_work = None
-        if self.distributed:
+        if self.distributed and use_aux:
             # this rank's [n_tok, n_examples] go behind the gradients NOW: they depend on the targets only
             local = dp.local_counts(targets, model.target_pad_idx)
             self.flat_grad[n:n + 2].copy_(local)
-            if use_aux and global_counts is None:
+            if global_counts is None:
                 global_counts, counts_work = dp.start_count_allreduce(targets, model.target_pad_idx, self.group)
         # Off the critical path, on a second stream beside the forward pass: the zeroing of the gradient buffer
         # (ModelForward.backward is told so below) and - without the auxiliary task - d(loss)/d(logp), which depends on the
@@ -125,8 +125,21 @@ class FusedTrainer:
             if early_grad:
                 d_logp, _ = ops.nll_grad_from_targets(targets, V, model.target_pad_idx, 1, sum_form=self.distributed,
                                                       d_logp=self._d_logp, out=self._count_out)
-        logp, aux = model(commands_input=commands, commands_lengths=commands_lengths, situations_input=situations,
-                          target_batch=targets, target_lengths=target_lengths)
+                if self.distributed:
+                    # this rank's [n_tok, n_examples] behind the gradients (two copies, nothing allocated): the token count
+                    # is the one gscan_nll_count has just produced
+                    self.flat_grad[n:n + 1].copy_(self._count_out[1:2])
+                    self.flat_grad[n + 1:n + 2].copy_(dp.batch_const(targets))
+                d_ready = torch.cuda.Event()
+                d_ready.record(side)
+        if early_grad:
+            # ... and the forward call runs the output-head backward too, most of it beside the decoder sweep
+            ops.set_early_dlogp(d_logp, d_ready)
+        try:
+            logp, aux = model(commands_input=commands, commands_lengths=commands_lengths, situations_input=situations,
+                              target_batch=targets, target_lengths=target_lengths)
+        finally:
+            ops.set_early_dlogp(None)
         main.wait_stream(side)
         if early_grad:
             fwd_done = torch.cuda.Event()

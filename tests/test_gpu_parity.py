@@ -12,7 +12,7 @@ import multimodal_seq2seq_gscan_b200 as pkg
 from multimodal_seq2seq_gscan_b200 import ops
 from oracle import gscan_oracle as O
 from tests.golden_util import CASE_NAMES, load_case
-from tests.gpu_util import DEV, build_model, oracle_run, rel_l2, to_dev
+from tests.gpu_util import DEV, build_model, full_state_dict, oracle_run, rel_l2, to_dev
 
 pytestmark = pytest.mark.gpu
 
@@ -453,6 +453,54 @@ def test_ragged_batch_sizes_and_lengths():
         named = dict(model.named_parameters())
         for pname, _ in O.param_shapes(cfg):
             assert rel_l2(named[pname].grad, grads_o[pname]) <= GRAD_RTOL, (B, pname)
+
+
+@pytest.mark.parametrize("aux", [False, True])
+def test_fused_trainer_gradient_equals_autograd_path(aux):
+    """FusedTrainer forms d(loss)/d(logp) from the targets before the forward pass and lets gscan_forward_train run the
+    output-head backward inside the forward call (no auxiliary task), or takes the plain autograd path (auxiliary task):
+    either way its flat gradient must be the gradient of `get_loss (+ 0.3 get_auxiliary_loss)` through Model, the path
+    the golden tests pin against the reference.  Dropout off so that both passes see the same network."""
+    from multimodal_seq2seq_gscan_b200.trainer import FusedTrainer
+    cfg = dict(O.CONFIGS["comp"])
+    cfg["auxiliary_task"] = aux
+    params = O.synthetic_params(cfg, 11, scale=1.5)
+    batch = O.synthetic_batch(cfg, batch_size=24, seed=12, max_tgt_len=33)
+    d = to_dev(batch)
+    kw = O.model_kwargs(cfg)
+    for k in list(kw):
+        if "dropout" in k:
+            kw[k] = 0.0
+
+    def make():
+        m = pkg.Model(**kw).to(DEV)
+        m.load_state_dict(full_state_dict(params), strict=True)
+        m.train(True)
+        return m
+
+    ref = make()
+    logp, a = ref(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"], situations_input=d["situations"],
+                  target_batch=d["targets"], target_lengths=batch["tgt_lengths"])
+    loss = ref.get_loss(logp, d["targets"])
+    if aux:
+        loss = loss + 0.3 * ref.get_auxiliary_loss(a, d["positions"])
+    loss.backward()
+    model = make()
+    trainer = FusedTrainer(model, weight_target_loss=0.3)
+    out = trainer.train_step(d["commands"], batch["cmd_lengths"], d["situations"], d["targets"], batch["tgt_lengths"],
+                             d["positions"] if aux else None)
+    assert abs(out.item() - loss.item()) <= 1e-5 * max(1.0, abs(loss.item()))
+    views = trainer._views(trainer.last_flat_grad)
+    for (name, pr), g in zip(ref.named_parameters(), views):
+        assert rel_l2(g, pr.grad) <= 2e-6, name
+    # and a second step on the trainer's persistent buffers gives the same gradient from the same parameters
+    model2 = make()
+    t2 = FusedTrainer(model2, weight_target_loss=0.3, learning_rate=0.0)
+    for _ in range(2):
+        t2.train_step(d["commands"], batch["cmd_lengths"], d["situations"], d["targets"], batch["tgt_lengths"],
+                      d["positions"] if aux else None)
+    for (name, pr), g in zip(ref.named_parameters(), t2._views(t2.last_flat_grad)):
+        assert rel_l2(g, pr.grad) <= 2e-6, name
 
 
 def test_adam_step_matches_torch():
