@@ -21,7 +21,7 @@ gradients and loss normalisers when N>1) + Adam.  Rank 0 prints ONE JSON line.
             the library on the same stream (gscan_profile).  The sweep is a latency-bound recurrence (121
             dependent steps): the object carries the (tiny, honest) fraction of the measured tensor peak, and
             the figure that means something - microseconds per decoder step against a per-phase latency model
-            of the critical path (profiles/r02_latency_model.md) - plus the ncu numbers of the shipping kernels.
+            of the critical path (profiles/r02_ncu_sweeps.md) - plus the ncu numbers of the shipping kernels.
   decode    batched greedy decoding (configs[3]): device-timed value, e2e from pinned host inputs with the
             tokens and lengths copied back, us per decoding step, the reference's batch-1 predict() timed on
             the host cores beside it; with --gpus N every rank decodes its own replica batch.
@@ -671,7 +671,7 @@ def main():
             "note": "recurrence: 121 dependent steps x ~12 dependent phases per step inside a 5-CTA cluster; neither the "
                     "tensor pipe nor HBM bounds it (see `ncu`), the dependent chain does.  Figure of merit: "
                     "us_per_decoder_step against critical_path_us_model (per-phase latency model, "
-                    "profiles/r02_latency_model.md).  Mat-vecs run on mma.sync tf32 in split precision (3 MMAs per "
+                    "profiles/r02_ncu_sweeps.md).  Mat-vecs run on mma.sync tf32 in split precision (3 MMAs per "
                     "fp32-accurate product).",
             "kernel_ms": bwd_ms, "us_per_decoder_step": bwd_us,
             "critical_path_us_model": model.get("bwd_us"),

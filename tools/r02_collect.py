@@ -122,9 +122,9 @@ if os.path.exists(lc) and os.path.exists(bj):
     rows = list(csv.reader(open(lc, errors="replace")))
     hdr = next(r for r in rows if "Kernel Name" in r)
     out = [dict(zip(hdr, r)) for r in rows if len(r) == len(hdr) and r[0] != "ID"]
-    ad = [i for i, d in enumerate(out) if "adam_kernel" in d["Kernel Name"]]
+    ad = [i for i, d in enumerate(out) if "dec_fwd_v3" in d["Kernel Name"]]
     if len(ad) >= 2:
-        step = out[ad[-2] + 1:ad[-1] + 1]
+        step = out[ad[0]:ad[1]]          # one training step, forward sweep to forward sweep
         agg = collections.OrderedDict()
         for d in step:
             n = re.sub(r"\(.*", "", d["Kernel Name"])
@@ -144,7 +144,7 @@ if os.path.exists(lc) and os.path.exists(bj):
             for n, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write("| %.1f | %d | %.1f %% | %s |\n" % (us, c, 100 * us / tot, n))
             f.write("| **%.1f** | **%d** | | one step, %d of them ours |\n" % (tot, sum(v[0] for v in agg.values()),
-                                                                             sum(v[0] for k, v in agg.items() if "gscan" in k)))
+                                                                             sum(v[0] for k, v in agg.items() if "at::" not in k)))
 
 # ---- sanitizer ----------------------------------------------------------------------------------------------------------------
 san = []
