@@ -118,7 +118,7 @@ void chain_report(const char* title) {
 struct SideStreams {
   cudaStream_t s[3] = {nullptr, nullptr, nullptr};   // [0], [1]: high priority chains; [2]: shadow work, lowest priority
   cudaEvent_t fork_ev[3] = {nullptr, nullptr, nullptr}, join_ev[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};   // forward pass: [0] command encoder done, [1] Wcomb, [2] encoder about to start
+  cudaEvent_t aux_ev[3] = {nullptr, nullptr, nullptr};   // forward pass: [0] command encoder done, [1] Wcomb; backward: [1] gradient destinations zeroed
   bool ok = false;
 };
 SideStreams* side_streams() {
@@ -432,10 +432,6 @@ int run_cnn_forward(const gscan_dims& d, const float* const* P, const float* sit
       const_cast<float*>(P[GSCAN_P_CONV3_W]), Wt, 1);
   GSCAN_CHECK_LAUNCH();
   size_t smem = (size_t)cs.M() * cs.C * 8;
-  // GSCAN_CNN_SMEM_KB: ask for more shared memory than the kernel uses, which bounds its CTAs per SM (8 of them fill
-  // every thread slot of an SM for ~35 us each, and the small kernels of the encoder chain queue behind them)
-  static const int pad_kb = env_int("GSCAN_CNN_SMEM_KB", 0);
-  if (pad_kb > 0 && smem < (size_t)pad_kb * 1024) smem = (size_t)pad_kb * 1024;
   if (smem > 48 * 1024) TRY(set_smem(cnn_forward_kernel, smem));
   const int ysplit = max(1, min(8, ceil_div(cs.M() * cs.D(), 3 * 256)));   // ~3 outputs per thread
   cnn_forward_kernel<<<dim3(d.B, ysplit), 256, smem, st>>>(cs, situations, Wt, P[GSCAN_P_CONV1_B], P[GSCAN_P_CONV2_B],
@@ -456,19 +452,10 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
   SideStreams* S = cnn_stream_given ? nullptr : side_streams();
   cudaStream_t sc = cnn_stream_given ? cnn_stream : (S ? S->s[0] : st);
   if (S) TRY(fork_side(S, 0, st));
-  // GSCAN_CNN_AFTER=1: the CNN starts when the encoder's recurrent kernel does (its 1600 CTAs otherwise take every
-  // thread slot of the chip for ~40 us and the small kernels at the head of the encoder chain queue behind them)
-  static const bool cnn_after = env_int("GSCAN_CNN_AFTER", 0) != 0;
-  SideStreams* SE = side_streams();
-  const bool defer_cnn = cnn_after && SE && sc != st;
-  auto cnn_chain = [&]() -> int {
-    TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, sc));
-    chain_mark("cnn", sc);
-    if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, sc));
-    chain_mark("KV", sc);
-    return 0;
-  };
-  if (!defer_cnn) TRY(cnn_chain());
+  TRY(run_cnn_forward(d, P, situations, drop_cnn, ws + L.Wt_cnn, ws + L.feat, sc));
+  chain_mark("cnn", sc);
+  if (need_keys) TRY(linear(ws + L.feat, D, P[GSCAN_P_VIS_KEY_W], D, ws + L.KV, H, B * M, H, D, nullptr, nullptr, 0, sc));
+  chain_mark("KV", sc);
   // weight packing and the zero fills first: the chip is still empty then; behind the input GEMMs they queued for
   // SM slots behind the CNN's CTAs (a 2 us fill took 15 us: tools/step_trace.py)
   {
@@ -503,13 +490,8 @@ int run_encoder_side(const gscan_dims& d, const float* const* P, const long long
   ep.len = cmd_len;
   ep.enc_out = ws + L.enc_out;
   ep.h_enc = ws + L.h_enc;
-  if (defer_cnn) {
-    TRYCUDA(cudaEventRecord(SE->aux_ev[2], st));
-    TRYCUDA(cudaStreamWaitEvent(sc, SE->aux_ev[2], 0));
-  }
   TRY(launch_enc(d, ep, false, st));
   chain_mark("enc_fwd", st);
-  if (defer_cnn) TRY(cnn_chain());
   // with `enc_done` the caller runs what else hangs off the encoder outputs (initial decoder state, P table) on other
   // streams, beside the textual keys
   if (enc_done) TRYCUDA(cudaEventRecord(enc_done, st));
@@ -1081,11 +1063,9 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
 
   prof_mark(0, st);
   chain_mark("fwd_start", st);
-  TRYCUDA(cudaMemsetAsync(ws + L.progress_f, 0, 4 * sizeof(unsigned int), st));   // progress words of the sweep (far ahead of it)
   // gscan_forward_train: the output-head backward runs inside this call (fused kernel only: V <= kHeadMaxV, H <= 128)
   early_head_set(ws, nullptr);
   const bool early_head = d_logp_early != nullptr && V <= kHeadMaxV && H <= 128 && getenv("GSCAN_HEAD_UNFUSED") == nullptr;
-  if (early_head) TRYCUDA(cudaMemsetAsync(ws + L.dWh2o, 0, sizeof(float) * (size_t)V * H, st));
   // Three chains before the sweep: the command encoder (a long chain of small kernels: high-priority helper stream 1,
   // issued first), the decoder prelude (depends on targets and weights only; one big GEMM, capped: high-priority
   // helper stream 0) and the situation CNN (wide kernels of small CTAs that co-reside with the GEMM's: the caller's
@@ -1095,15 +1075,18 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   cudaStream_t se = S ? S->s[1] : st, sp = S ? S->s[0] : st;
   // GSCAN_FWD_SCHED: 0 = round-1 schedule (K^T, h0, P one after the other behind the encoder);  1 = the three products
   // that hang off the encoder outputs run side by side (K^T on the encoder's stream, h0 on the prelude's, P - straight
-  // from enc_out through Wcomb - on the caller's);  2 = and the prelude GEMM waits for the encoder: the encoder's
-  // 100 CTAs and the GEMM's persistent CTAs both need an SM's whole shared memory, and a GEMM that got there first
-  // made the encoder run in two waves (55 us instead of 31: tools/step_trace.py)
+  // from enc_out through Wcomb - on the caller's).  (Holding the prelude GEMM back until the encoder is done - its
+  // persistent CTAs and the encoder's 100 CTAs exclude each other on an SM, and the encoder then runs in one wave, 31
+  // instead of 55 us - ended later overall: profiles/r02_negative_results.md.)
   static const int sched = env_int("GSCAN_FWD_SCHED", 1);
   const bool par_tail = S && sched >= 1 && v3_shape_ok(*d);
   if (S) {
     TRY(fork_side(S, 1, st));
     TRY(fork_side(S, 0, st));
   }
+  // (behind the forks: the helper chains do not wait for these fills)
+  TRYCUDA(cudaMemsetAsync(ws + L.progress_f, 0, 4 * sizeof(unsigned int), st));   // progress words of the sweep (far ahead of it)
+  if (early_head) TRYCUDA(cudaMemsetAsync(ws + L.dWh2o, 0, sizeof(float) * (size_t)V * H, st));
   if (par_tail) {   // weights only, ahead of the prelude (which has slack)
     TRY(compute_Wcomb(*d, P, ws + L.Wcomb, sp));
     TRYCUDA(cudaEventRecord(S->aux_ev[1], sp));
@@ -1131,9 +1114,7 @@ int forward_impl(const gscan_dims* d, const float* const* P, const int64_t* comm
   float* U1 = ws + L.U + (size_t)B * 4 * H;
   // input-gate pre-activations of every step at once: Xe = E . W_ih[:, :H]^T + b_ih + b_hh
   {
-    const bool after_enc = par_tail && sched >= 2;
-    if (after_enc) TRYCUDA(cudaStreamWaitEvent(sp, S->aux_ev[0], 0));
-    tc::ScopedSmCap cap(S && !after_enc ? cap_prelude() : 0);   // leave SMs to the command encoder running beside it
+    tc::ScopedSmCap cap(S ? cap_prelude() : 0);   // leave SMs to the command encoder running beside it
     TRY(linear(U1, 4 * H, P[GSCAN_P_DEC_WIH], 3 * H, ws + L.Xe, 4 * H, Tt * B, 4 * H, H, P[GSCAN_P_DEC_BIH],
                P[GSCAN_P_DEC_BHH], 0, sp));
   }
