@@ -503,6 +503,51 @@ def test_fused_trainer_gradient_equals_autograd_path(aux):
         assert rel_l2(g, pr.grad) <= 2e-6, name
 
 
+def test_early_loss_gradient_is_bit_identical_and_head_fallback_is_safe():
+    """(1) d(loss)/d(logp) formed from the targets alone (gscan_nll_count + gscan_nll_backward) is bit-identical to what
+    autograd returns through NLLLoss, in mean form and in the SUM form of the data-parallel step.  (2) A forward pass
+    that was given an early d_logp (gscan_forward_train: the output-head backward runs inside the forward call) followed
+    by a backward pass with ANOTHER gradient recomputes the head: gradients equal the plain path's."""
+    cfg = dict(O.CONFIGS["comp"])
+    params = O.synthetic_params(cfg, 21, scale=1.5)
+    batch = O.synthetic_batch(cfg, batch_size=16, seed=22, max_tgt_len=27)
+    d = to_dev(batch)
+    model = build_model(cfg, params, train=True)
+    logp, _ = model(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"], situations_input=d["situations"],
+                    target_batch=d["targets"], target_lengths=batch["tgt_lengths"])
+    V = logp.shape[2]
+    lp = logp.detach().clone().requires_grad_(True)
+    nll, n_tok = ops.NLLLoss.apply(lp, d["targets"], 0, 1)
+    (g_mean,) = torch.autograd.grad(nll, lp, retain_graph=True)
+    (g_sum,) = torch.autograd.grad(nll * n_tok.detach(), lp)
+    e_mean, out = ops.nll_grad_from_targets(d["targets"], V, 0, 1, sum_form=False)
+    e_sum, _ = ops.nll_grad_from_targets(d["targets"], V, 0, 1, sum_form=True)
+    assert torch.equal(e_mean, g_mean) and torch.equal(e_sum, g_sum)
+    assert out[1].item() == n_tok.item()
+
+    def grads_with(early, w):
+        m = build_model(cfg, params, train=True)
+        if early is not None:
+            ops.set_early_dlogp(early)
+        try:
+            lg, _ = m(commands_input=d["commands"], commands_lengths=batch["cmd_lengths"], situations_input=d["situations"],
+                      target_batch=d["targets"], target_lengths=batch["tgt_lengths"])
+        finally:
+            ops.set_early_dlogp(None)
+        gs = torch.autograd.grad([lg], list(m.parameters()), grad_outputs=[w])
+        return lg.detach(), [g.clone() for g in gs]
+
+    torch.manual_seed(3)
+    w = torch.randn_like(logp) * 0.01
+    lp0, g0 = grads_with(None, w)                       # plain path
+    lp1, g1 = grads_with(e_mean, w)                     # early head for e_mean, then a backward pass with w: recomputed
+    lp2, g2 = grads_with(w, w)                          # early head for w, backward with the same tensor: skipped there
+    assert torch.equal(lp0, lp1) and torch.equal(lp0, lp2)
+    for a, b_, c in zip(g0, g1, g2):
+        assert rel_l2(b_, a) <= 1e-6
+        assert rel_l2(c, a) <= 2e-6
+
+
 def test_adam_step_matches_torch():
     torch.manual_seed(0)
     n = 100003
