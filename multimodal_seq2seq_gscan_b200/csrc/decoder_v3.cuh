@@ -766,33 +766,58 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
                  bytes_xV = (uint32_t)(kC * kNB * kM * 4);
   bool finished_early = false;   // greedy: every sequence of this cluster ended before the step limit
   // greedy (predict.py:106-117), run by warp 15: wait for the logit partial sums of step s (X7), pick the token of each
-  // live example (lane n), update tok / alive / the any-alive flag; lane-private my_len / my_steps of lanes < kNB
+  // live example, update tok / alive / the any-alive flag; lane-private my_len / my_steps of lanes < kNB.
+  // Four lanes per example (lane = n + 8 u takes the vocabulary entries u, u + 4, ...): the pick runs beside the stage-A
+  // mat-vecs of the next step and must not outlast them (one lane per example: 45 dependent shared-memory loads).
   auto greedy_pick = [&](int s) {
     mbar_wait(bar0 + 8u * 5, (uint32_t)(s & 1));
     if (lane == 0 && s + 1 < p.T) mbar_arm(bar0 + 8u * 5, (uint32_t)(kC * kNB * p.V * 4));   // for step s + 1
+    const int n = lane & (kNB - 1), u = lane >> 3, V = p.V;
+    const bool live = alive_s[n] != 0;
+    const int tok = tok_s[n];
+    float l[8];   // V <= 32 in greedy mode (checked on the host): <= 8 entries per lane
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = u + 4 * i;
+      float a = -INFINITY;
+      if (live && v < V) {
+        a = outE_s[tok * V + v];
+#pragma unroll
+        for (int r = 0; r < kC; ++r) a += xL_s[(r * kNB + n) * V + v];
+      }
+      l[i] = a;
+      mx = fmaxf(mx, a);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (live && u + 4 * i < V) sum += expf(l[i] - mx);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    const float lse = logf(sum);
+    float best = -INFINITY;   // first maximum of the log-softmax values, as F.log_softmax(...).max(dim=-1) gives
+    int arg = 1 << 30;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = u + 4 * i;
+      if (live && v < V) {
+        const float lp = (l[i] - mx) - lse;
+        if (lp > best) { best = lp; arg = v; }
+      }
+    }
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    __syncwarp();   // every lane has read alive / tok of its example
     int alive_now = 0;
     if (lane < kNB) {
-      const int n = lane, V = p.V;
-      if (alive_s[n]) {
-        const int tok = tok_s[n];
-        float l[32];   // V <= 32 in greedy mode (checked on the host)
-        float mx = -INFINITY;
-        for (int v = 0; v < V; ++v) {
-          float a = outE_s[tok * V + v];
-#pragma unroll
-          for (int r = 0; r < kC; ++r) a += xL_s[(r * kNB + n) * V + v];
-          l[v] = a;
-          mx = fmaxf(mx, a);
-        }
-        float sum = 0.f;
-        for (int v = 0; v < V; ++v) sum += expf(l[v] - mx);
-        const float lse = logf(sum);
-        float best = -INFINITY;   // first maximum of the log-softmax values, as F.log_softmax(...).max(dim=-1) gives
-        int arg = 0;
-        for (int v = 0; v < V; ++v) {
-          const float lp = (l[v] - mx) - lse;
-          if (lp > best) { best = lp; arg = v; }
-        }
+      if (live) {
         my_steps++;
         if (arg == p.eos) {
           alive_s[n] = 0;
