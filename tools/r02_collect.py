@@ -67,7 +67,48 @@ if tl:
                 "`GSCAN_TIMELINE=<prefix> python bench.py --steps 2 ...` (tools/r02_final.sh); stamps are `clock64` of lane 0 of every "
                 "warp of CTA 0 (template flag TL: the production kernels carry none of it).  Stamp numbers: GSCAN3_STAMP(k) in "
                 "csrc/decoder_v3.cuh / decoder_v3_bwd.cuh.\n\n```\n")
-        f.write("\n".join(l for l in err.splitlines() if l.startswith("[gscan]")) + "\n```\n\n")
+        glines = [l for l in err.splitlines() if l.startswith("[gscan]")]
+        f.write("\n".join(glines[-4:]) + "\n```\n\n")
+
+        def phases(tag):
+            for l in reversed(glines):
+                if ("v3 %s timeline" % tag) in l:
+                    return [float(x.split(":")[1]) for x in l.split("):")[1].split() if ":" in x and x.split(":")[0].isdigit()]
+            return None
+
+        # warp 0's time between consecutive stamps, grouped into the phases of the latency model (r02_ncu_sweeps.md)
+        fwd_map = [("X6 wait (h gather of the previous step)", [0], 700), ("stage A: [q_T; W_c h; W_hh h] mat-vecs, epilogue, hand-off", [1], 496),
+                   ("text scores (tanh) and X1 send", [2], 350), ("X1 wait", [3], 685), ("text softmax, barrier", [4], 450),
+                   ("P combination: q', gate and c_T contributions, X3 send", [5], 200), ("X3 wait (q' gather)", [6], 700),
+                   ("stage C: q_V = W_qV q'", [7], 328), ("visual scores (5760 tanh) and X4 send", [8], 960), ("X4 wait", [9], 899),
+                   ("visual softmax, c_V slice, X5 send", [10], 660), ("X5 wait (c_V gather)", [11], 700),
+                   ("stage D: W_ih[:, 2H:3H] c_V, barrier", [12], 496), ("LSTM cell, X6 send, hand-off to the I/O warps", [13, 14, 15], 200)]
+        bwd_map = [("tanh of both attentions recomputed; X_d wait (dh of the previous step)", [0, 1], 1040), ("B1 cell backward, barrier", [2], 250),
+                   ("B2 W_ih[:, 2H:3H]^T da (X_e send), W_hh^T da deferred", [3], 630), ("B3 dalpha part 1", [4], 0),
+                   ("X_e wait, B4 dc_V assembled, partial dbeta, X_a send", [5, 6], 1000), ("X_a wait, B5 visual softmax backward", [7], 1249),
+                   ("B6 visual key path", [8], 350), ("B7 W_qV^T dq_V, X_b send", [9], 294), ("X_b wait, dd", [10], 700),
+                   ("B9 dalpha completed, X_c send", [11], 300), ("X_c wait, B10 text softmax backward", [12], 1035),
+                   ("B11 text key path", [13], 300), ("B12 W_qT^T dq_T, dh reduce-scatter (X_d send)", [14, 15], 294)]
+        for tag, name, mp in (("fwd", "Forward", fwd_map), ("bwd", "Backward", bwd_map)):
+            ph = phases(tag)
+            if not ph:
+                continue
+            f.write("## %s sweep: warp 0 between consecutive stamps against the latency model (cycles per decoder step)\n\n"
+                    "| phase | measured | model |\n|---|---:|---:|\n" % name)
+            tm = tmod = 0.0
+            for label, idx, mod in mp:
+                m = sum(ph[i] for i in idx)
+                tm += m
+                tmod += mod
+                f.write("| %s | %.0f | %s |\n" % (label, m, mod if mod else "(off the modelled path)"))
+            f.write("| **total** | **%.0f** | **%.0f** |\n\n" % (tm, tmod))
+        f.write("Reading: the exchanges themselves (the `wait` rows) are AT or below the measured constants - the receiver has other "
+                "work while the messages fly - and the model's gap sits in the compute phases: stage A and the score phases cost 2-3 x "
+                "their issue-rate bound because the warps that own a phase also wait at block barriers for the others (ncu: 0.9-1.3 warps "
+                "per issue stalled at barriers, issue slots 34-41 % busy, `profiles/r02_ncu_sweeps.md`), and the visual-score phase "
+                "(11.5 k MUFU operations per step on four schedulers with a 3-2-2-2 warp split) is the largest single item of the "
+                "forward step.  The model is a lower bound for this decomposition, not a fit: measured / model = 1.4 (forward), "
+                "1.8 (backward).\n\n")
         f.write("\n".join(tl))
 
 # ---- pipelined chain times + host probe, appended to the step trace --------------------------------------------------------
