@@ -108,7 +108,10 @@ if tl:
                 "per issue stalled at barriers, issue slots 34-41 % busy, `profiles/r02_ncu_sweeps.md`), and the visual-score phase "
                 "(11.5 k MUFU operations per step on four schedulers with a 3-2-2-2 warp split) is the largest single item of the "
                 "forward step.  The model is a lower bound for this decomposition, not a fit: measured / model = 1.4 (forward), "
-                "1.8 (backward).\n\n")
+                "1.8 (backward).\n\nCaveat for the per-warp tables below: a stamp placed right AFTER a block barrier shows when the "
+                "warp ARRIVED at it, not when it was released - the clock read has no dependence on the barrier and is scheduled ahead "
+                "of it (forward stamps 5 and 13: warps 0-7 'pass' the stage-D barrier 600 cycles before warps 8-12, which run stage D, "
+                "arrive).  The release time of a barrier is the latest arrival in its row.\n\n")
         f.write("\n".join(tl))
 
 # ---- pipelined chain times + host probe, appended to the step trace --------------------------------------------------------
