@@ -156,19 +156,39 @@ __device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, ui
 // One 16-row tile: o = W[16 x 112] . x[8 examples][112]^T.  Lane (g = lane>>2, t = lane&3) supplies for k-step s the
 // operand slots (k = 2t, 2t+1 | 2t+8, 2t+9) from the physical columns (16s + 4t, +1 | +2, +3), for A and B alike, so
 // that B comes from ONE 16-byte load.  Result layout as mv_tile: o[0], o[1] = row g, examples 2t, 2t+1; o[2], o[3] = row g + 8.
+// PIPE: loads of step s + 1 ahead of the MMAs of step s (training sweep: -7 us; the greedy sweep, with its other register
+// budget, lost 1 % with it and keeps the plain order).
+template <bool PIPE = true>
 __device__ __forceinline__ void mv_tile16(const uint32_t (&whi)[kK16][4], const uint4* __restrict__ wlo_lane,
                                           const float* __restrict__ x_lane, float (&o)[4]) {
   float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+  // software-pipelined by one k-step: the two 16-byte shared-memory loads of step s + 1 are issued before the MMAs of
+  // step s (left to itself the compiler put every load right in front of its first use: a load-to-use stall per k-step,
+  // ~800 cycles per stage in the per-warp timeline against ~330 of tensor time)
+  float4 xv = lds4(x_lane);
+  uint4 lo = wlo_lane[0];
 #pragma unroll
   for (int s = 0; s < kK16; ++s) {
-    const float4 xv = lds4(x_lane + 16 * s);
-    const uint4 lo = wlo_lane[s * 32];
+    float4 xn = xv;
+    uint4 ln = lo;
+    if (PIPE && s + 1 < kK16) {
+      xn = lds4(x_lane + 16 * (s + 1));
+      ln = wlo_lane[(s + 1) * 32];
+    }
+    if (!PIPE && s > 0) {
+      xv = lds4(x_lane + 16 * s);
+      lo = wlo_lane[s * 32];
+      xn = xv;
+      ln = lo;
+    }
     uint32_t bh0, bl0, bh1, bl1;
     split_f16x2(xv.x, xv.y, bh0, bl0);
     split_f16x2(xv.z, xv.w, bh1, bl1);
     mma_f16(d0, whi[s][0], whi[s][1], whi[s][2], whi[s][3], bh0, bh1);
     mma_f16(d1, lo.x, lo.y, lo.z, lo.w, bh0, bh1);
     mma_f16(d2, whi[s][0], whi[s][1], whi[s][2], whi[s][3], bl0, bl1);
+    xv = xn;
+    lo = ln;
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) o[j] = fmaf(kLoInv, d1[j] + d2[j], d0[j]);
@@ -849,7 +869,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     GSCAN3_STAMP(1);
     // ---- stage A: everything that depends only on h_{t-1} ---------------------------------------------
     float o[4] = {0.f, 0.f, 0.f, 0.f};
-    if (roleA) mv_tile16(whi, wlo_lane, hfull_s + fg * kXS + 4 * ft, o);
+    if (roleA) mv_tile16<!GREEDY>(whi, wlo_lane, hfull_s + fg * kXS + 4 * ft, o);
     GSCAN3_STAMP(16);
     if (GREEDY) {
       // The token of the previous step is picked HERE, by the otherwise idle warp 15, while the role-A warps run the
@@ -1020,7 +1040,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
       GSCAN3_STAMP(7);
       if (roleC) {
         float o[4];
-        mv_tile16(whi, wlo_lane, qpfull_s + fg * kXS + 4 * ft, o);
+        mv_tile16<!GREEDY>(whi, wlo_lane, qpfull_s + fg * kXS + 4 * ft, o);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = lr0 + 8 * (j >> 1), n = nF + (j & 1);
@@ -1118,7 +1138,7 @@ __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1) dec_fw
     // ---- stage D: c_V contribution to the gates, then the LSTM cell ---------------------------------------
     if (roleD) {
       float o[4];
-      mv_tile16(whi, wlo_lane, cvfull_s + fg * kXS + 4 * ft, o);
+      mv_tile16<!GREEDY>(whi, wlo_lane, cvfull_s + fg * kXS + 4 * ft, o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) g_s[(nF + (j & 1)) * kGS + lr0 + 8 * (j >> 1)] += o[j];
     }
