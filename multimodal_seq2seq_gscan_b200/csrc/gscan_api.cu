@@ -400,7 +400,7 @@ int env_int(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 int cap_prelude() { static const int c = env_int("GSCAN_CAP_PRELUDE", 96); return c; }
-int cap_post() { static const int c = env_int("GSCAN_CAP_POST", 120); return c; }
+int cap_post() { static const int c = env_int("GSCAN_CAP_POST", 80); return c; }
 
 int check_common(const gscan_dims* d, const float* const* params) {
   if (!d || !params) return GSCAN_E_BADARG;
