@@ -43,6 +43,7 @@ if "--impl=reference" in sys.argv or ("--impl" in sys.argv and sys.argv[sys.argv
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import argparse
+import gc
 import json
 import statistics
 import subprocess
@@ -426,7 +427,9 @@ class Workload:
 
 
 def measure_training(wl, steps, warmup, flush, barrier, dist, lib):
-    """(ms per step [max over ranks of per-step CUDA-event times], launches) with the batch resident."""
+    """(ms per step [max over ranks of per-step CUDA-event times], launches) with the batch resident.
+    The Python garbage collector is run before the barrier and switched off inside the timed loop (a generation-2 pass is
+    1-2 ms of host time, enough to drain the launch queue once in a few dozen steps)."""
     for _ in range(warmup):
         wl.step_resident()
     barrier()
@@ -435,12 +438,17 @@ def measure_training(wl, steps, warmup, flush, barrier, dist, lib):
     launches0 = lib.gscan_launch_count()
     if wl.distributed:
         wl.trainer.collective_events = []
+    gc.collect()
+    gc.disable()          # no collector pauses inside the timed region (a generation-2 pass is 1-2 ms of host time)
     barrier()
-    for i in range(steps):
-        flush.zero_()
-        starts[i].record()
-        wl.step_resident()
-        ends[i].record()
+    try:
+        for i in range(steps):
+            flush.zero_()
+            starts[i].record()
+            wl.step_resident()
+            ends[i].record()
+    finally:
+        gc.enable()
     barrier()
     launches = lib.gscan_launch_count() - launches0
     per_step = [s.elapsed_time(e) for s, e in zip(starts, ends)]
