@@ -375,11 +375,13 @@ class NLLLoss(torch.autograd.Function):
 
 
 def nll_grad_from_targets(targets: torch.Tensor, V: int, pad_idx: int, shift: int, sum_form: bool,
-                          d_logp: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+                          d_logp: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                          d_loss: Optional[torch.Tensor] = None):
     """d(loss)/d(logp) of the mean (``sum_form`` False) or the sum of the NLL terms ``NLLLoss`` scores, formed from the
     targets alone (gscan_nll_count + gscan_nll_backward) - bit-identical to what ``NLLLoss.backward`` returns for
     ``loss = mean`` resp. ``loss = mean * count``.  Returns (d_logp [B, T, V], result buffer with the count at [1]);
-    ``d_logp`` / ``out`` may be handed in (buffers a caller reuses from step to step)."""
+    ``d_logp`` / ``out`` may be handed in (buffers a caller reuses from step to step); ``d_loss`` overrides the factor
+    (the weight of an auxiliary loss term)."""
     lib = _lib.load()
     _require_cuda(targets)
     targets = targets.contiguous()
@@ -390,7 +392,8 @@ def nll_grad_from_targets(targets: torch.Tensor, V: int, pad_idx: int, shift: in
     _lib.check(lib.gscan_nll_count(_ptr(targets), B, T, int(pad_idx), int(shift), _ptr(out), _stream(dev)), "gscan_nll_count")
     if d_logp is None or d_logp.shape != (B, T, V):
         d_logp = torch.empty(B, T, V, dtype=torch.float32, device=dev)
-    d_loss = out[1:2] if sum_form else _ones1(dev)     # d loss / d mean = count, resp. 1
+    if d_loss is None:                                  # (a 1-element device tensor: d loss / d mean of these terms)
+        d_loss = out[1:2] if sum_form else _ones1(dev)  # d loss / d mean = count, resp. 1
     _lib.check(lib.gscan_nll_backward(_ptr(targets), B, T, V, int(pad_idx), int(shift), _ptr(out), _ptr(d_loss), _ptr(d_logp),
                                       _stream(dev)), "gscan_nll_backward")
     _call_counts["other"] += 2

@@ -47,6 +47,9 @@ class FusedTrainer:
         self._side_stream = torch.cuda.Stream(device=dev)   # zeroing, early loss gradient, loss value (train_step)
         self._d_logp = None
         self._count_out = None
+        self._d_aux = None
+        self._aux_count_out = None
+        self._aux_scale = None
         self._one = torch.ones((), dtype=torch.float32, device=dev)   # d loss / d loss, without a fill kernel per step
         # re-seat every parameter as a view into the flat buffer (identity of the nn.Parameter kept)
         with torch.no_grad():
@@ -60,6 +63,11 @@ class FusedTrainer:
     def _views(self, flat):
         return [flat[int(o):int(o) + n].view(s) for s, o, n in zip(self._shapes, self._offsets[:-1], self._sizes)
                 if s is not None]
+
+    @staticmethod
+    def _aux_cells(model, situations) -> int:
+        """Number of grid cells the auxiliary head scores (model.py:166-170: one log-probability per cell)."""
+        return int(situations.shape[1] * situations.shape[2])
 
     def current_lr(self) -> float:
         """LambdaLR(lr_decay ** (t / lr_decay_steps)) with t = optimizer steps taken so far (train.py:69-70)."""
@@ -110,7 +118,10 @@ class FusedTrainer:
         # beside the backward pass.
         main = torch.cuda.current_stream(self.flat_param.device)
         side = self._side_stream
-        early_grad = not use_aux
+        # (with the auxiliary task the SUM form needs the ratio N_tok / B of the GLOBAL batch: known in advance when the
+        #  caller passed the counts as numbers, else the plain autograd path runs)
+        early_grad = (not use_aux) or (not self.distributed) or \
+            (global_counts is not None and not isinstance(global_counts[0], torch.Tensor))
         side.wait_stream(main)           # the previous step's Adam has read the gradient buffer; the targets are there
         # (nothing is ALLOCATED under the second stream: blocks that cross streams come back to the caching allocator
         #  late, and the cudaMalloc calls that then fill the gap showed up as 40-80 ms stalls every few dozen steps)
@@ -120,6 +131,18 @@ class FusedTrainer:
                 self._d_logp = torch.empty(targets.shape[0], targets.shape[1], V, dtype=torch.float32, device=targets.device)
                 self._count_out = torch.empty(68, dtype=torch.float32, device=targets.device)
             loss_out = torch.empty(68, dtype=torch.float32, device=targets.device)   # fresh: the caller may keep the loss
+            if use_aux:
+                pos = target_positions.view(-1, 1)
+                Bp, Ma = pos.shape[0], self._aux_cells(model, situations)
+                if self._d_aux is None or self._d_aux.shape != (Bp, 1, Ma):
+                    self._d_aux = torch.empty(Bp, 1, Ma, dtype=torch.float32, device=targets.device)
+                    self._aux_count_out = torch.empty(68, dtype=torch.float32, device=targets.device)
+                    self._aux_scale = torch.empty(1, dtype=torch.float32, device=targets.device)
+                aux_out = torch.empty(68, dtype=torch.float32, device=targets.device)
+                # d loss / d (mean auxiliary NLL): its weight, times B_local * N_tok_all / B_all in the SUM form (dp.sum_loss)
+                aux_w = float(self.weight_target_loss)
+                if self.distributed:
+                    aux_w *= targets.shape[0] * (float(global_counts[0]) / float(global_counts[1]))
         with torch.cuda.stream(side):
             self.flat_grad[:n].zero_()
             if early_grad:
@@ -132,6 +155,10 @@ class FusedTrainer:
                     self.flat_grad[n + 1:n + 2].copy_(dp.batch_const(targets))
                 d_ready = torch.cuda.Event()
                 d_ready.record(side)
+                if use_aux:      # the auxiliary head's loss gradient, from the target positions alone (model.py:59,162-164)
+                    self._aux_scale.fill_(aux_w)
+                    d_aux, _ = ops.nll_grad_from_targets(pos, Ma, -100, 0, sum_form=False, d_logp=self._d_aux,
+                                                         out=self._aux_count_out, d_loss=self._aux_scale)
         if early_grad:
             # ... and the forward call runs the output-head backward too, most of it beside the decoder sweep
             ops.set_early_dlogp(d_logp, d_ready)
@@ -146,12 +173,18 @@ class FusedTrainer:
             fwd_done.record(main)
             ops.set_flat_grad_target(self.flat_grad, prezeroed=True)
             try:
-                grads = torch.autograd.grad([logp], self._present, grad_outputs=[d_logp])
+                if use_aux:
+                    grads = torch.autograd.grad([logp, aux], self._present, grad_outputs=[d_logp, d_aux.view_as(aux)])
+                else:
+                    grads = torch.autograd.grad([logp], self._present, grad_outputs=[d_logp])
             finally:
                 ops.set_flat_grad_target(None)
+            aux_mean = None
             with torch.cuda.stream(side), torch.no_grad():
                 side.wait_event(fwd_done)
                 nll, n_tok = ops.NLLLoss.apply(logp.detach(), targets, model.target_pad_idx, 1, False, loss_out)
+                if use_aux:
+                    aux_mean = ops.NLLLoss.apply(aux.detach().unsqueeze(1), pos, -100, 0, False, aux_out)[0]
             loss = None      # formed on the caller's stream once it has waited for the second one (below)
         else:
             nll, n_tok = ops.NLLLoss.apply(logp, targets, model.target_pad_idx, 1, False)
@@ -186,7 +219,10 @@ class FusedTrainer:
                       self.eps, self.step_count, grad_denom=denom)
         main.wait_stream(side)           # the loss value (and nothing else) comes from the second stream
         if loss is None:
-            loss = nll * n_tok if self.distributed else nll
+            if self.distributed:
+                loss = dp.sum_loss(nll, n_tok, aux_mean, targets.shape[0], self.weight_target_loss, global_counts)
+            else:
+                loss = dp.global_loss(nll, aux_mean, self.weight_target_loss)
         model.update_state(is_best=False)
         self.last_logp, self.last_aux = logp.detach(), aux
         self.last_flat_grad = flat_grad
